@@ -1,0 +1,142 @@
+/*
+ * slgpu.h -- C-ABI of the B200 parallel-tempering engine (libslgpu.so).
+ *
+ * Drop-in boundary for the src/infer hot path of NICTA/stateline.  What each entry point stands in
+ * for on the reference side (paths relative to the reference root):
+ *
+ *   slgpu_create        StatelineSettings::fromJSON (src/app/serverwrapper.hpp:64-91) +
+ *                       ProposalBoundsFromJSON (src/infer/sampler.hpp:34-60) + the construction half of
+ *                       runSampler (src/app/serverwrapper.cpp:48-55): adapters, proposal, chain array.
+ *                       The likelihood comes from a plugin .so (slgpu_plugin.h) instead of
+ *                       WorkerWrapper(LikelihoodFn, ...) (src/app/workerwrapper.hpp:21-31).
+ *   slgpu_init_chains   the initialisation loop, src/app/serverwrapper.cpp:60-81.
+ *   slgpu_step_rounds   n canonical rounds of Sampler::step() (src/infer/sampler.cpp:142-203): every
+ *                       chain of every stack appends once per round.
+ *   slgpu_run           the main loop and stop rule of runSampler (src/app/serverwrapper.cpp:100-134):
+ *                       initialise, step until #cold-chain samples >= nSamplesTotal, flush the sink.
+ *   slgpu_drain         ChainArray::flushToDisk / CSVChainArrayWriter::append (src/infer/chainarray.cpp:131-155,
+ *                       src/db/db.cpp:37-47): hands the caller the cold-chain rows
+ *                       x_0..x_{d-1},energy,sigma,beta,accepted,swapType in emission order.
+ *   slgpu_rhat          EPSRDiagnostic::rHat (src/infer/diagnostics.cpp:49-71).
+ *   slgpu_get_*         what TableLogger prints (src/infer/logging.cpp:35-87): per-chain counters,
+ *                       sigma, beta; plus adapter / shaper state for parity tests.
+ *
+ * Error convention: the reference exits the process on a missing config key
+ * (src/app/jsonsettings.hpp:22-35) and LOG(FATAL)s on bound-size mismatch (sampler.hpp:42-46).  Nothing
+ * here exits or throws across the ABI: every call returns slgpu_status and slgpu_last_error() holds a
+ * message for the calling thread.  There is no CPU fallback: without a CUDA device slgpu_create fails
+ * with SLGPU_E_CUDA.
+ *
+ * Ownership: the engine owns all device memory, its streams and the host ring it allocates; the caller
+ * owns the config string, the payload (copied at create) and any buffer it passes in.  An engine
+ * handle is not thread-safe.
+ */
+#ifndef SLGPU_H
+#define SLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slgpu_engine slgpu_engine;
+
+typedef enum slgpu_status {
+  SLGPU_OK = 0,
+  SLGPU_E_CONFIG = 1, /* missing / malformed key, bound-size mismatch, unsupported sizes */
+  SLGPU_E_PLUGIN = 2, /* plugin .so missing, wrong ABI, wrong job-type / dimension count */
+  SLGPU_E_CUDA = 3,   /* no device, allocation or launch failure */
+  SLGPU_E_ARG = 4,    /* NULL or out-of-range argument */
+  SLGPU_E_STATE = 5,  /* call not valid in the engine's current state */
+  SLGPU_E_IO = 6,     /* output directory / file failure */
+  SLGPU_E_FULL = 7    /* host ring cannot take the rows of the requested rounds: drain first */
+} slgpu_status;
+
+/* message of the last failing call on this thread ("" if none) */
+const char* slgpu_last_error(void);
+/* "slgpu <version> sm_100a" */
+const char* slgpu_version(void);
+
+/*
+ * config_json: the stateline server config, same keys as src/app/serverwrapper.hpp:64-91, all
+ * mandatory except "initial" (needed when useInitial is true):
+ *   nStacks nTemperatures nSamplesTotal swapInterval loggingRateSec nJobTypes outputPath
+ *   optimalAcceptRate optimalSwapRate useInitial [initial] min max
+ * plus an optional "gpu" object:
+ *   device (int, default 0)           seed (default 1234)        stackOffset (default 0)
+ *   rng "philox" | "replay"           sink "device" | "host" | "csv" | "none" (default "device")
+ *   adaptInterval (default swapInterval)   maxRoundsPerLaunch (default 64)
+ *   hostRingRounds (default 8 * rounds per launch)   overwrite (bool, default false)
+ * plugin_path: likelihood plugin .so; plugin_entry: its table symbol (NULL = "slgpu_plugin_entry").
+ * payload: POD handed to the functor's constructor, copied to the device (may be NULL).
+ */
+slgpu_status slgpu_create(const char* config_json, const char* plugin_path, const char* plugin_entry,
+                          const void* payload, size_t payload_bytes, slgpu_engine** out);
+void slgpu_destroy(slgpu_engine* e);
+
+/* recorded draws for rng "replay" (host pointers, copied to the device):
+ * z[n_rounds][C][d], u_mh[n_rounds][C], u_swap[n_rounds][C] (indexed by the lower chain of the pair),
+ * x_init[C][d] pre-bounce initial points.  C = nStacks * nTemperatures, chain id = stack*T + temp. */
+slgpu_status slgpu_set_replay(slgpu_engine* e, const double* z, const double* u_mh, const double* u_swap,
+                              const double* x_init, uint64_t n_rounds);
+
+slgpu_status slgpu_init_chains(slgpu_engine* e);
+/* enqueue n rounds (asynchronous; returns once the launches and sink copies are queued) */
+slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds);
+/* wait for everything queued so far; reports asynchronous CUDA errors */
+slgpu_status slgpu_sync(slgpu_engine* e);
+/* the reference's whole run: init (if needed), ceil(nSamplesTotal / nStacks) rounds, flush the sink */
+slgpu_status slgpu_run(slgpu_engine* e);
+uint64_t slgpu_rounds_done(const slgpu_engine* e);
+
+/* ---- cold-chain rows (sink "host"): emission order is round-major, stack-minor; the first nStacks
+ * rows are the initial states.  Row = d + 5 doubles (src/db/db.cpp:18-25). ---- */
+slgpu_status slgpu_drain(slgpu_engine* e, double* rows, size_t cap_rows, size_t* n_rows);
+/* zero-copy view of the pinned host ring: landed-but-unconsumed rows as up to two spans */
+slgpu_status slgpu_peek(slgpu_engine* e, const double** span0, size_t* n0, const double** span1, size_t* n1);
+slgpu_status slgpu_advance(slgpu_engine* e, size_t n_rows);
+uint64_t slgpu_rows_emitted(const slgpu_engine* e); /* rows produced on the device so far */
+
+/* ---- device-side timing of what was queued between the two calls (CUDA events on the compute stream) ---- */
+slgpu_status slgpu_timer_start(slgpu_engine* e);
+slgpu_status slgpu_timer_stop(slgpu_engine* e, double* elapsed_ms); /* waits for the stop event */
+uint64_t slgpu_launch_count(const slgpu_engine* e);                 /* kernels launched so far */
+
+/* ---- state inspection (synchronises) ---- */
+uint32_t slgpu_n_dims(const slgpu_engine* e);
+uint32_t slgpu_n_chains(const slgpu_engine* e);
+/* rows[C][d+5]: last row of every chain */
+slgpu_status slgpu_get_last_rows(slgpu_engine* e, double* rows);
+slgpu_status slgpu_get_sigma_beta(slgpu_engine* e, double* sigma, double* beta);
+/* dense row-major d*d L and N of one chain (either may be NULL) and the shaper count */
+slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double* N, double* count);
+/* tier models: which = 0 sigma, 1 beta; mu_xx[T][9], mu_xy[T][3], weight[T][3], count[T] (any may be NULL) */
+slgpu_status slgpu_get_models(slgpu_engine* e, int which, double* mu_xx, double* mu_xy, double* weight,
+                              double* count);
+slgpu_status slgpu_get_ladder(slgpu_engine* e, double* ladder);
+/* TableLogger counters per chain (src/infer/logging.cpp:29-48); any pointer may be NULL */
+slgpu_status slgpu_get_counters(slgpu_engine* e, uint64_t* length, uint64_t* accepts, uint64_t* swaps,
+                                uint64_t* swap_attempts, double* min_energy);
+/* EPSR per dimension over this engine's stacks (diagnostics.cpp:49-71) */
+slgpu_status slgpu_rhat(slgpu_engine* e, double* rhat);
+/* sharded EPSR: stage 1 returns sum_s M_s per dim and the stack / sample counts; after the caller
+ * has all-reduced them, stage 2 returns sum_s (M_s - mean)^2 and sum_s S_s per dim for a second
+ * all-reduce; slgpu_rhat_finish applies diagnostics.cpp:58-70 to the reduced sums. */
+slgpu_status slgpu_rhat_stage1(slgpu_engine* e, double* sum_m, double* n_stacks, double* n_samples);
+slgpu_status slgpu_rhat_stage2(slgpu_engine* e, const double* mean, double* sum_dm2, double* sum_s);
+void slgpu_rhat_finish(const double* sum_dm2, const double* sum_s, double n_stacks_total, double n_samples,
+                       uint32_t d, double* rhat);
+/* end-of-run summary as JSON: per-tier accept / swap rates, sigma, beta, R-hat, rounds, rows */
+slgpu_status slgpu_summary(slgpu_engine* e, char* json, size_t cap, size_t* needed);
+
+/* contract check: nll[point*J + job] = f(job, x[point*d ..]) through the plugin's functor (host buffers) */
+slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_points, double* nll);
+/* one State row as CSVChainArrayWriter prints it (db.cpp:18-25), no newline; returns the length */
+size_t slgpu_format_row(const double* row, uint32_t d, char* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

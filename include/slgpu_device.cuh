@@ -1,0 +1,567 @@
+/*
+ * slgpu_device.cuh -- the parallel-tempering step kernels (sm_100a), templated on the user's
+ * likelihood functor.  Included by plugin translation units only (see slgpu_plugin.h).
+ *
+ * What it replaces in NICTA/stateline: the body of Sampler::step() (src/infer/sampler.cpp:142-203)
+ * and everything it calls -- GaussianProposal::propose + bouncyBounds (sampler.cpp:23-93),
+ * the likelihood round trip (src/comms/requester.cpp:27-57 -> user LikelihoodFn, workerwrapper.hpp:21),
+ * ChainArray::append/acceptProposal/swap/acceptSwap (src/infer/chainarray.cpp:30-67,94-189),
+ * the per-row half of RegressionAdapter::update/predict/computeSigma (src/infer/adaptive.cpp:63-139),
+ * ProposalShaper::update (adaptive.cpp:173-209), the TableLogger counters (src/infer/logging.cpp:35-48),
+ * EPSRDiagnostic::update (src/infer/diagnostics.cpp:27-47) and the cold-chain row sink
+ * (chainarray.cpp:131-155, src/db/db.cpp:18-47).
+ *
+ * Likelihood contract (device form of `double f(uint jobType, const std::vector<double>& x)`):
+ *
+ *     struct MyLik {
+ *       __device__ explicit MyLik(const void* payload);   // payload: POD copied to the device by the engine
+ *       __device__ double operator()(uint32_t job_type, const double* x, uint32_t d) const;  // negative log-likelihood
+ *     };
+ *
+ * pure, re-entrant, no allocation; +inf means "certain reject" (chainarray.cpp:36-37).  The energy of
+ * a sample is the sum over job types in job-type order (sampler.cpp:148-150).
+ *
+ * Mapping: one thread per chain, the T chains of a stack in T adjacent lanes of one warp (floor(32/T)
+ * stacks per warp), so the hot->cold swap sweep of a stack runs on warp shuffles.  All arithmetic is
+ * fp64.  Compile with -fmad=false: products and sums round separately except where fma() is written,
+ * which is exactly the operation order of the CPU oracle, so + - * / sqrt fma agree bit for bit.
+ */
+#ifndef SLGPU_DEVICE_CUH
+#define SLGPU_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slgpu_plugin.h"
+
+#ifndef SLGPU_THREADS
+#define SLGPU_THREADS 128
+#endif
+
+namespace slgpu {
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+/* ---- Philox4x32-10, counter layout of the oracle (oracle/sl_oracle.cpp philox_draw) ---- */
+__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const u32 h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const u32 n0 = h1 ^ c1 ^ k0;
+    const u32 n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* two uniforms strictly inside (0,1): u = (k52 + 0.5) * 2^-52 */
+__device__ __forceinline__ void philox_draw(u64 seed, u32 chain, u64 round, u32 purpose, u32 block, double& ua, double& ub) {
+  u32 o[4];
+  philox4x32_10((u32)round, chain, (purpose & 0xffu) | ((u32)(round >> 32) << 8), block, (u32)seed, (u32)(seed >> 32), o);
+  const u64 a = (((u64)o[1] << 32) | o[0]) >> 12;
+  const u64 b = (((u64)o[3] << 32) | o[2]) >> 12;
+  ua = ((double)a + 0.5) * 2.220446049250313080847263336181640625e-16;
+  ub = ((double)b + 0.5) * 2.220446049250313080847263336181640625e-16;
+}
+
+/* std::max / std::min comparison order (NaN handling as on the host) */
+__device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }
+
+/* bouncyBounds, one coordinate -- src/infer/sampler.cpp:23-56 */
+__device__ __forceinline__ double bounce1(double v, double mn, double mx) {
+  const double delta = mx - mn;
+  double result = v;
+  if (v > mx) {
+    const double overstep = v - mx;
+    const int nSteps = (int)(overstep / delta);
+    const double stillToGo = overstep - nSteps * delta;
+    result = (nSteps % 2 == 0) ? mx - stillToGo : mn + stillToGo;
+  }
+  if (v < mn) {
+    const double understep = mn - v;
+    const int nSteps = (int)(understep / delta);
+    const double stillToGo = understep - nSteps * delta;
+    result = (nSteps % 2 == 0) ? mn + stillToGo : mx - stillToGo;
+  }
+  return result;
+}
+
+/* RegressionAdapter::predict -- src/infer/adaptive.cpp:94-106 */
+__device__ __forceinline__ double predict(const double* w, double opt, double min_cap, double max_cap, double side) {
+  const double eps = 1e-3;
+  const double denom = smax(eps, w[0]);
+  double numer = -(opt - w[1] * side - w[2]);
+  numer = smax(smin(numer, denom * max_cap), denom * min_cap);
+  return numer / denom;
+}
+
+/* one sample of the regression sufficient statistics (model half of adaptive.cpp:63-75, summed form) */
+template <int STRIDE>
+__device__ __forceinline__ void stats_accumulate(double* P, double min_cap, double max_cap, double logval, double side, bool acc) {
+  logval = smin(smax(logval, min_cap), max_cap);
+  const double x0 = -logval, x1 = side, y = acc ? 1.0 : 0.0;
+  P[0 * STRIDE] += x0 * x0;
+  P[1 * STRIDE] += x0 * x1;
+  P[2 * STRIDE] += x0;
+  P[3 * STRIDE] += x1 * x1;
+  P[4 * STRIDE] += x1;
+  P[5 * STRIDE] += 1.0;
+  P[6 * STRIDE] += x0 * y;
+  P[7 * STRIDE] += x1 * y;
+  P[8 * STRIDE] += y;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+/* ProposalShaper::update -- src/infer/adaptive.cpp:173-209 on the packed lower triangle L(r,k) =
+ * Lc[(r(r+1)/2+k)*ls]; xs holds the accepted jump on entry.  Returns the new N scale. */
+template <int D>
+__device__ __forceinline__ double shaper_update(double* __restrict__ Lc, size_t ls, int d_rt, double* xs, double& count, double prop_norm) {
+  constexpr int DM = D > 0 ? D : (int)SLGPU_MAX_DIMS;
+  const int d = D > 0 ? D : d_rt;
+  const double eps = 1e-18;
+  count += 1.0;
+  const double sq = sqrt(count);
+  const double scale = sqrt((count - 1.0) / count);
+  double fr[DM]; /* per-row sums of squares, left to right */
+#pragma unroll
+  for (int i = 0; i < d; ++i) {
+    xs[i] = xs[i] / sq;
+    fr[i] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < d; ++k) {
+    const size_t kk = (size_t)(k * (k + 1) / 2 + k) * ls;
+    const double Lkk = Lc[kk] * scale;
+    const double V = smax(eps, Lkk);
+    const double r = sqrt(V * V + xs[k] * xs[k]);
+    const double c = r / V;
+    const double s = xs[k] / V;
+    Lc[kk] = r;
+    fr[k] = fma(r, r, fr[k]);
+#pragma unroll
+    for (int j = k + 1; j < d; ++j) {
+      const size_t jk = (size_t)(j * (j + 1) / 2 + k) * ls;
+      double Ljk = Lc[jk] * scale;
+      Ljk = (Ljk + s * xs[j]) / c;
+      Lc[jk] = Ljk;
+      xs[j] = c * xs[j] - s * Ljk;
+      fr[j] = fma(Ljk, Ljk, fr[j]);
+    }
+  }
+  /* |L|_F in the oracle's canonical order: slot l sums rows l, l+32, ...; halving tree over 32 slots */
+  double slot[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) slot[l] = 0.0;
+#pragma unroll
+  for (int r = 0; r < d; ++r) slot[r & 31] += fr[r];
+  int nlive = d < 32 ? d : 32;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+    for (int l = 0; l < m; ++l)
+      if (l + m < nlive) slot[l] += slot[l + m]; /* slots >= nlive are +0: adding them is the identity */
+    if (nlive > m) nlive = m;
+  }
+  const double frob = sqrt(slot[0]);
+  return prop_norm / smax(frob, eps);
+}
+
+struct ThreadMap {
+  int T, lane, sl, t, base, spw;
+  u32 s, c;
+  bool active;
+  __device__ ThreadMap(const slgpu_step_params& p) {
+    T = (int)p.n_temps;
+    spw = 32 / T;
+    lane = threadIdx.x & 31;
+    sl = lane / T;
+    t = lane - sl * T;
+    const u32 gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    s = gw * (u32)spw + (u32)sl;
+    active = (sl < spw) && (s < p.n_stacks);
+    if (sl >= spw) { /* idle tail lanes of a warp: keep every shuffle source inside the warp */
+      base = lane;
+      t = 0;
+    } else {
+      base = sl * T;
+    }
+    c = s * (u32)T + (u32)t;
+  }
+};
+
+/* --------------------------------------------------------------------------------------------
+ * pt_init: chain initialisation, src/app/serverwrapper.cpp:60-81 + generateInitialSample :21-41,
+ * ProposalShaper ctor adaptive.cpp:155-171, ChainArray::initialise chainarray.cpp:123-129,
+ * TableLogger ctor logging.cpp:29-33.
+ * ------------------------------------------------------------------------------------------ */
+template <class Lik, int D>
+__global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step_params p) {
+  constexpr int DM = D > 0 ? D : (int)SLGPU_MAX_DIMS;
+  const int d = D > 0 ? D : (int)p.n_dims;
+  const ThreadMap m(p);
+  if (!m.active) return;
+  const size_t C = (size_t)p.n_stacks * p.n_temps;
+  const u32 c = m.c;
+  const u32 gchain = p.stack_offset * p.n_temps + c;
+  const Lik lik(p.payload);
+  double x[DM];
+  if (p.initial) {
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+      x[i] = p.initial[i];
+  } else if (p.rng_mode == SLGPU_RNG_REPLAY) {
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+      x[i] = p.rp_xinit[(size_t)c * d + i];
+  } else { /* VectorXd::Random(d): uniform in [-1,1] */
+#pragma unroll
+    for (int k = 0; k < (d + 1) / 2; ++k) {
+      double ua, ub;
+      philox_draw(p.seed, gchain, 0, 3, (u32)k, ua, ub);
+      x[2 * k] = 2.0 * ua - 1.0;
+      if (2 * k + 1 < d) x[2 * k + 1] = 2.0 * ub - 1.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < d; ++i)
+    x[i] = bounce1(x[i], p.mn[i], p.mx[i]);
+  double e = 0.0;
+  for (u32 j = 0; j < p.n_job_types; ++j) e += lik(j, x, (u32)d);
+#pragma unroll
+  for (int i = 0; i < d; ++i)
+    p.x[(size_t)i * C + c] = x[i];
+  for (int r = 0; r < d; ++r)
+    for (int k = 0; k <= r; ++k)
+      p.L[(size_t)(r * (r + 1) / 2 + k) * C + c] = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
+  const double b = p.ladder[m.t];
+  p.energy[c] = e;
+  p.row_sigma[c] = 1.0;
+  p.row_beta[c] = b;
+  p.sigma[c] = 1.0;
+  p.beta[c] = b;
+  p.nscale[c] = 0.0; /* unused until the first shaper update */
+  p.sh_count[c] = p.sh_count0;
+  p.accepted[c] = 1;
+  p.swap_type[c] = 0;
+  p.lg_accepts[c] = 1;
+  p.lg_swaps[c] = 0;
+  p.lg_swap_attempts[c] = 1;
+  p.lg_min_energy[c] = __longlong_as_double(0x7ff0000000000000LL);
+  for (int k = 0; k < 9; ++k) {
+    p.p_sig[(size_t)k * C + c] = 0.0;
+    p.p_beta[(size_t)k * C + c] = 0.0;
+  }
+  if (m.t == 0) {
+    for (int i = 0; i < d; ++i) {
+      p.ep_m[(size_t)i * p.n_stacks + m.s] = 0.0;
+      p.ep_s[(size_t)i * p.n_stacks + m.s] = 0.0;
+    }
+    if (p.rows_out) { /* the initial state is row 0 of the stack's output (chainarray.cpp:123-129) */
+      double* row = p.rows_out + (size_t)m.s * (d + SLGPU_ROW_EXTRA);
+      for (int i = 0; i < d; ++i) row[i] = x[i];
+      row[d] = e; row[d + 1] = 1.0; row[d + 2] = b; row[d + 3] = 1.0; row[d + 4] = 0.0;
+    }
+  }
+}
+
+/* --------------------------------------------------------------------------------------------
+ * pt_step: n_rounds canonical rounds.  Round r (0-based; chain length becomes r+2):
+ *   propose -> energy -> MH accept -> sigma statistics + new sigma -> shaper update,
+ *   then, when (r+2) % swapInterval == 0, the hot->cold swap sweep of every stack, the beta
+ *   statistics and the ladder refresh, then counters / EPSR / cold-row emission.
+ * The tier models (sig_w, ladder) are frozen for the launch ("batched" schedule of the oracle).
+ * ------------------------------------------------------------------------------------------ */
+template <class Lik, int D>
+__global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step_params p) {
+  constexpr int DM = D > 0 ? D : (int)SLGPU_MAX_DIMS;
+  const int d = D > 0 ? D : (int)p.n_dims;
+  const ThreadMap m(p);
+  const int T = m.T;
+  const size_t C = (size_t)p.n_stacks * p.n_temps;
+  const u32 c = m.active ? m.c : 0u; /* idle lanes shadow chain 0 for loads and never store */
+  const u32 gchain = p.stack_offset * p.n_temps + c;
+  const bool active = m.active;
+
+  __shared__ double s_mn[DM], s_mx[DM], s_n0[DM];
+  __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
+  __shared__ double s_P[18 * SLGPU_THREADS];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    s_mn[i] = p.mn[i];
+    s_mx[i] = p.mx[i];
+    s_n0[i] = p.n0_diag[i];
+  }
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    s_w[3 * i + 0] = p.sig_w[3 * i + 0];
+    s_w[3 * i + 1] = p.sig_w[3 * i + 1];
+    s_w[3 * i + 2] = p.sig_w[3 * i + 2];
+    s_lad[i] = p.ladder[i];
+  }
+  double* P = s_P + threadIdx.x; /* P[k*SLGPU_THREADS], k<9 sigma statistics, 9..17 beta statistics */
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    P[k * SLGPU_THREADS] = p.p_sig[(size_t)k * C + c];
+    P[(9 + k) * SLGPU_THREADS] = p.p_beta[(size_t)k * C + c];
+  }
+  __syncthreads();
+
+  const Lik lik(p.payload);
+  double* __restrict__ Lc = p.L + c;
+  const size_t ls = C;
+
+  double x[DM];
+#pragma unroll
+  for (int i = 0; i < d; ++i)
+    x[i] = p.x[(size_t)i * C + c];
+  double energy = p.energy[c], row_sigma = p.row_sigma[c], row_beta = p.row_beta[c];
+  double sigma = p.sigma[c], beta = p.beta[c], nscale = p.nscale[c], sh_count = p.sh_count[c];
+  int accepted = p.accepted[c], swap_type = p.swap_type[c];
+  u32 lg_accepts = p.lg_accepts[c], lg_swaps = p.lg_swaps[c], lg_att = p.lg_swap_attempts[c];
+  double lg_min_e = p.lg_min_energy[c];
+  const double w3[3] = {s_w[3 * m.t], s_w[3 * m.t + 1], s_w[3 * m.t + 2]};
+  const int W = (int)p.swap_interval;
+
+  for (u32 it = 0; it < p.n_rounds; ++it) {
+    const u64 r = p.round_begin + it;
+    if (active) {
+      /* ---- proposal: x' = bounce(x + N z sigma), GaussianProposal::propose sampler.cpp:79-93 ---- */
+      double z[DM];
+      if (p.rng_mode == SLGPU_RNG_REPLAY) {
+        const double* zr = p.rp_z + ((size_t)r * C + c) * d;
+#pragma unroll
+        for (int i = 0; i < d; ++i)
+          z[i] = zr[i];
+      } else {
+#pragma unroll
+        for (int k = 0; k < (d + 1) / 2; ++k) {
+          double ua, ub;
+          philox_draw(p.seed, gchain, r, 0, (u32)k, ua, ub);
+          const double R = sqrt(-2.0 * log(ua));
+          const double th = 6.283185307179586476925286766559 * ub;
+          double sn, cs;
+          sincos(th, &sn, &cs);
+          z[2 * k] = R * cs;
+          if (2 * k + 1 < d) z[2 * k + 1] = R * sn;
+        }
+      }
+      const bool fresh = (sh_count == p.sh_count0); /* N still the constructor's diag(range/|range|) */
+      double xp[DM];
+#pragma unroll
+      for (int i = 0; i < d; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(Lc[(size_t)(i * (i + 1) / 2 + k) * ls] * nscale, z[k], acc);
+        const double nii = fresh ? s_n0[i] : Lc[(size_t)(i * (i + 1) / 2 + i) * ls] * nscale + 1e-4;
+        acc = fma(nii, z[i], acc);
+        xp[i] = bounce1(x[i] + acc * sigma, s_mn[i], s_mx[i]);
+      }
+      /* ---- energy: sum over job types in order, sampler.cpp:148-150 ---- */
+      double e_new = 0.0;
+      for (u32 j = 0; j < p.n_job_types; ++j) e_new += lik(j, xp, (u32)d);
+      /* ---- acceptProposal chainarray.cpp:30-45, append :94-121 ---- */
+      bool acc = false;
+      if (!isinf(e_new)) {
+        double u;
+        if (p.rng_mode == SLGPU_RNG_REPLAY) u = p.rp_umh[(size_t)r * C + c];
+        else { double ub; philox_draw(p.seed, gchain, r, 1, 0, u, ub); }
+        const double deltaEnergy = e_new - energy;
+        const double pr = exp(-1.0 * beta * deltaEnergy);
+        acc = u < pr;
+      }
+      if (acc) {
+#pragma unroll
+        for (int i = 0; i < d; ++i) {
+          const double nx = xp[i];
+          xp[i] = nx - x[i]; /* xp now holds the accepted jump (sampler.cpp:166) */
+          x[i] = nx;
+        }
+        energy = e_new;
+        row_sigma = sigma;
+        row_beta = beta;
+      }
+      accepted = acc ? 1 : 0;
+      swap_type = 0;
+      /* ---- sigma adaptation, sampler.cpp:160-162 (statistics summed, model frozen) ---- */
+      const double logtemper = -log(row_beta);
+      stats_accumulate<SLGPU_THREADS>(P, -8.0, 4.0, log(row_sigma), logtemper, acc);
+      sigma = exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
+      /* ---- proposal shape, sampler.cpp:165-166 ---- */
+      if (acc) nscale = shaper_update<D>(Lc, ls, d, xp, sh_count, p.prop_norm);
+    }
+
+    /* ---- swap sweep, hottest pair first: sampler.cpp:169-199,237-257, chainarray.cpp:55-67,162-189 ---- */
+    double mid_e = energy; /* the state step() returns for this chain: after its swap with the chain */
+    int mid_acc = accepted; /* above, before the swap with the chain below */
+    const bool swapRound = (T > 1) && ((r + 2) % (u64)W == 0);
+    if (swapRound) {
+      double u_sw = 0.0;
+      if (active && m.t < T - 1) {
+        if (p.rng_mode == SLGPU_RNG_REPLAY) u_sw = p.rp_uswap[(size_t)r * C + c];
+        else { double ub; philox_draw(p.seed, gchain, r, 2, 0, u_sw, ub); }
+      }
+      int cur = T - 1, my_src = m.t, mid_src = m.t;
+      bool my_swapped = false;
+      for (int tt = T - 2; tt >= 0; --tt) {
+        const double El = shfl_d(energy, m.base + tt);
+        const double Eh = shfl_d(energy, m.base + cur);
+        const double bl = shfl_d(beta, m.base + tt);
+        const double bh = shfl_d(beta, m.base + tt + 1);
+        const double u = shfl_d(u_sw, m.base + tt);
+        const double deltaEnergy = El - Eh;
+        const double deltaBeta = bl - bh;
+        const bool sw = u < exp(deltaEnergy * deltaBeta);
+        if (m.t == tt + 1) my_src = sw ? tt : cur;
+        if (m.t == tt) { my_swapped = sw; mid_src = sw ? cur : tt; }
+        if (!sw) cur = tt;
+      }
+      if (m.t == 0) my_src = cur;
+      /* beta statistics of pair (t, t+1): betaUpdate adaptive.cpp:108-116 */
+      const double lb = log(beta);
+      const double lbh = shfl_d(lb, m.lane + 1 < 32 ? m.lane + 1 : m.lane);
+      mid_e = shfl_d(energy, m.base + mid_src);
+      mid_acc = __shfl_sync(0xffffffffu, accepted, m.base + mid_src);
+      /* the exchange moves sample, energy and accepted; sigma and beta stay (chainarray.cpp:176-178) */
+      const double new_e = shfl_d(energy, m.base + my_src);
+      const int new_acc = __shfl_sync(0xffffffffu, accepted, m.base + my_src);
+#pragma unroll
+      for (int i = 0; i < d; ++i)
+        x[i] = shfl_d(x[i], m.base + my_src);
+      energy = new_e;
+      accepted = new_acc;
+      if (m.t < T - 1) {
+        swap_type = my_swapped ? 1 : 2;
+        stats_accumulate<SLGPU_THREADS>(P + 9 * SLGPU_THREADS, 0.0, 4.0, lb - lbh, lb, my_swapped);
+      }
+      if (m.t > 0) beta = s_lad[m.t]; /* sampler.cpp:186 with the ladder of the last adapt point */
+    }
+
+    if (active) {
+      /* ---- TableLogger::update, logging.cpp:35-48 ---- */
+      lg_min_e = smin(lg_min_e, mid_e);
+      lg_accepts += (u32)mid_acc;
+      lg_swaps += (swap_type == 1);
+      lg_att += (swap_type != 0);
+      if (m.t == 0) {
+        /* ---- EPSRDiagnostic::update diagnostics.cpp:27-47; n_ counts the cold rows seen ---- */
+        const double nn = (double)(r + 1);
+        for (int i = 0; i < d; ++i) {
+          const size_t o = (size_t)i * p.n_stacks + m.s;
+          const double mo = p.ep_m[o];
+          const double xi = x[i];
+          const double newM = mo + (xi - mo) / nn;
+          p.ep_s[o] = p.ep_s[o] + (xi - mo) * (xi - newM);
+          p.ep_m[o] = newM;
+        }
+        /* ---- cold-chain row, db.cpp:18-25 layout ---- */
+        if (p.rows_out) {
+          double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (d + SLGPU_ROW_EXTRA);
+#pragma unroll
+          for (int i = 0; i < d; ++i)
+            row[i] = x[i];
+          row[d] = energy;
+          row[d + 1] = row_sigma;
+          row[d + 2] = row_beta;
+          row[d + 3] = (double)accepted;
+          row[d + 4] = (double)swap_type;
+        }
+      }
+    }
+  }
+
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+      p.x[(size_t)i * C + c] = x[i];
+    p.energy[c] = energy;
+    p.row_sigma[c] = row_sigma;
+    p.row_beta[c] = row_beta;
+    p.sigma[c] = sigma;
+    p.beta[c] = beta;
+    p.nscale[c] = nscale;
+    p.sh_count[c] = sh_count;
+    p.accepted[c] = accepted;
+    p.swap_type[c] = swap_type;
+    p.lg_accepts[c] = lg_accepts;
+    p.lg_swaps[c] = lg_swaps;
+    p.lg_swap_attempts[c] = lg_att;
+    p.lg_min_energy[c] = lg_min_e;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      p.p_sig[(size_t)k * C + c] = P[k * SLGPU_THREADS];
+      p.p_beta[(size_t)k * C + c] = P[(9 + k) * SLGPU_THREADS];
+    }
+  }
+}
+
+/* contract check: nll[point*J + job] = f(job, x[point]) */
+template <class Lik>
+__global__ void lik_eval_kernel(const slgpu_step_params p, const double* __restrict__ xs, u32 n_points, double* __restrict__ nll) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const Lik lik(p.payload);
+  double x[SLGPU_MAX_DIMS];
+  for (u32 k = 0; k < p.n_dims; ++k) x[k] = xs[(size_t)i * p.n_dims + k];
+  for (u32 j = 0; j < p.n_job_types; ++j) nll[(size_t)i * p.n_job_types + j] = lik(j, x, p.n_dims);
+}
+
+inline unsigned grid_for(const slgpu_step_params* p) {
+  const unsigned spw = 32u / p->n_temps;
+  const unsigned per_block = spw * (SLGPU_THREADS / 32);
+  return (p->n_stacks + per_block - 1) / per_block;
+}
+
+/* host launchers instantiated per (functor, compile-time dimension); D = 0 is the runtime-d kernel */
+template <class Lik, int D>
+int launch_init_t(const slgpu_step_params* p, void* stream) {
+  pt_init_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  return (int)cudaGetLastError();
+}
+template <class Lik, int D>
+int launch_step_t(const slgpu_step_params* p, void* stream) {
+  pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  return (int)cudaGetLastError();
+}
+template <class Lik>
+int launch_eval_t(const slgpu_step_params* p, const double* x, uint32_t n_points, double* nll, void* stream) {
+  if (n_points == 0) return 0;
+  lik_eval_kernel<Lik><<<(n_points + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, x, n_points, nll);
+  return (int)cudaGetLastError();
+}
+
+/* dispatch on the run-time dimension over a compile-time list of specialised dimensions */
+template <class Lik, int... Ds>
+struct Dispatch {
+  static int init(const slgpu_step_params* p, void* s) {
+    int rc = -1;
+    const bool hit = ((p->n_dims == (uint32_t)Ds ? (rc = launch_init_t<Lik, Ds>(p, s), true) : false) || ...);
+    return hit ? rc : launch_init_t<Lik, 0>(p, s);
+  }
+  static int step(const slgpu_step_params* p, void* s) {
+    int rc = -1;
+    const bool hit = ((p->n_dims == (uint32_t)Ds ? (rc = launch_step_t<Lik, Ds>(p, s), true) : false) || ...);
+    return hit ? rc : launch_step_t<Lik, 0>(p, s);
+  }
+};
+
+}  // namespace slgpu
+
+/* Defines a plugin table named `sym` for functor `Lik`; specialised (fully unrolled) kernels are built
+ * for the listed dimensions, every other dimension <= SLGPU_MAX_DIMS runs the runtime-d kernel. */
+#define SLGPU_DEFINE_PLUGIN(sym, Lik, plugin_name, n_jobs, n_dims_fixed, payload_size, ...)                       \
+  static int sym##_init(const slgpu_step_params* p, void* s) { return slgpu::Dispatch<Lik, ##__VA_ARGS__>::init(p, s); } \
+  static int sym##_step(const slgpu_step_params* p, void* s) { return slgpu::Dispatch<Lik, ##__VA_ARGS__>::step(p, s); } \
+  static int sym##_eval(const slgpu_step_params* p, const double* x, uint32_t n, double* o, void* s) {            \
+    return slgpu::launch_eval_t<Lik>(p, x, n, o, s);                                                              \
+  }                                                                                                               \
+  extern "C" const slgpu_plugin_v1* sym(void) {                                                                   \
+    static const slgpu_plugin_v1 table = {SLGPU_PLUGIN_ABI, plugin_name, n_jobs, n_dims_fixed, payload_size,      \
+                                          sym##_init,       sym##_step,  sym##_eval};                             \
+    return &table;                                                                                                \
+  }
+
+#endif

@@ -1,0 +1,109 @@
+/*
+ * slgpu_plugin.h -- binary interface between the engine (libslgpu.so) and a likelihood plugin .so.
+ *
+ * In NICTA/stateline a user likelihood is a host callback
+ *     typedef std::function<double(uint, const std::vector<double>&)> LikelihoodFn;   (src/app/workerwrapper.hpp:21)
+ * run by worker processes and reached through the Requester -> Delegator -> Worker -> Minion
+ * ZeroMQ round trip (src/comms/requester.cpp:27-57, src/app/workerwrapper.cpp:24-36).  On the GPU
+ * path the likelihood is a __device__ functor.  A plugin .so instantiates the step kernels of
+ * slgpu_device.cuh with its functor (so the functor inlines; no device function pointers, no -rdc)
+ * and exports a table of host launchers through
+ *     extern "C" const slgpu_plugin_v1* slgpu_plugin_entry(void);
+ * The engine dlopen()s the plugin, fills slgpu_step_params with device pointers it owns and calls
+ * the launchers on its compute stream.  Plain C, no CUDA or torch types in the signatures.
+ */
+#ifndef SLGPU_PLUGIN_H
+#define SLGPU_PLUGIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLGPU_PLUGIN_ABI 1u
+#define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
+#define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
+#define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
+
+enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
+
+/* Everything a launch needs.  All pointers are device pointers owned by the engine.
+ * Chain id = stack * n_temps + temperature, temperature 0 coldest (src/infer/chainarray.hpp:28-37).
+ * C = n_stacks * n_temps.  Per-chain arrays are indexed [chain]; vectors and matrices are stored
+ * structure-of-arrays, element-major: x[i * C + chain], L[(r*(r+1)/2 + k) * C + chain] (packed lower
+ * triangle, row-major), p_sig[k * C + chain], ep_m[i * n_stacks + stack]. */
+typedef struct slgpu_step_params {
+  uint32_t n_stacks, n_temps, n_dims, n_job_types;
+  uint32_t swap_interval;  /* swap sweep in the round that makes the chain length a multiple of it */
+  uint32_t stack_offset;   /* global index of local stack 0: Philox streams of a sharded run */
+  uint32_t n_rounds;       /* rounds this launch advances every chain by */
+  int32_t rng_mode;        /* SLGPU_RNG_* */
+  uint64_t seed;
+  uint64_t round_begin;    /* 0-based index of the first round of this launch */
+  uint64_t replay_rounds;  /* rounds held by the replay buffers */
+  double opt_accept;       /* optimalAcceptRate */
+  double sh_count0;        /* ProposalShaper initial_count (src/app/serverwrapper.cpp:50) */
+  double prop_norm;        /* |(max-min)/4| (src/infer/adaptive.cpp:163) */
+  const double* mn;        /* [d] */
+  const double* mx;        /* [d] */
+  const double* n0_diag;   /* [d] range/|range|: diagonal of the initial N (adaptive.cpp:164-169) */
+  const double* initial;   /* [d] or NULL (useInitial) */
+  /* chain state */
+  double* x;               /* [d][C]  sample of the last row */
+  double* L;               /* [d(d+1)/2][C]  ProposalShaper L_ (adaptive.cpp:158) */
+  double* energy;          /* [C] */
+  double* row_sigma;       /* [C] sigma stored in the last row (stale after a reject, chainarray.cpp:102-106) */
+  double* row_beta;        /* [C] */
+  double* sigma;           /* [C] ChainArray::sigma_ == RegressionAdapter::values_ */
+  double* beta;            /* [C] ChainArray::beta_ */
+  double* nscale;          /* [C] prop_norm / max(|L|_F, eps): N = L * nscale + 1e-4 I (adaptive.cpp:200-204) */
+  double* sh_count;        /* [C] ProposalShaper count_ */
+  int32_t* accepted;       /* [C] last row's accepted flag */
+  int32_t* swap_type;      /* [C] last row's swapType */
+  /* TableLogger counters (src/infer/logging.cpp:29-48) */
+  uint32_t* lg_accepts;
+  uint32_t* lg_swaps;
+  uint32_t* lg_swap_attempts;
+  double* lg_min_energy;
+  /* tier models, frozen while a launch runs */
+  const double* sig_w;     /* [T][3] weights of the sigma regression */
+  const double* ladder;    /* [T] beta ladder from the last adapt point */
+  /* regression sufficient statistics gathered since the last adapt point */
+  double* p_sig;           /* [9][C] */
+  double* p_beta;          /* [9][C] */
+  /* EPSRDiagnostic Welford state of the cold chains (src/infer/diagnostics.cpp:27-47) */
+  double* ep_m;            /* [d][S] */
+  double* ep_s;            /* [d][S] */
+  /* cold-chain rows of this launch: rows_out[(round - round_begin) * S + stack][d + 5], or NULL */
+  double* rows_out;
+  /* recorded draws (SLGPU_RNG_REPLAY): z[round][C][d], u_mh[round][C], u_swap[round][C], x_init[C][d] */
+  const double* rp_z;
+  const double* rp_umh;
+  const double* rp_uswap;
+  const double* rp_xinit;
+  const void* payload;     /* the plugin's POD payload, copied to the device by the engine */
+} slgpu_step_params;
+
+/* Launchers return a cudaError_t value (0 = success); stream is a cudaStream_t. */
+typedef struct slgpu_plugin_v1 {
+  uint32_t abi_version;  /* SLGPU_PLUGIN_ABI */
+  const char* name;
+  uint32_t n_job_types;  /* job types the likelihood is defined for; 0 = any */
+  uint32_t n_dims;       /* dimension the likelihood is defined for; 0 = any */
+  size_t payload_bytes;  /* expected payload size; 0 = none / variable */
+  /* chain initialisation (src/app/serverwrapper.cpp:60-81); writes the initial cold rows to rows_out[S][d+5] */
+  int (*launch_init)(const slgpu_step_params* p, void* stream);
+  /* n_rounds canonical rounds of Sampler::step for every chain (src/infer/sampler.cpp:142-203) */
+  int (*launch_step)(const slgpu_step_params* p, void* stream);
+  /* nll[point * J + job] = f(job, x[point * d ..]) for n_points points (point-major x): contract check */
+  int (*launch_eval)(const slgpu_step_params* p, const double* x, uint32_t n_points, double* nll, void* stream);
+} slgpu_plugin_v1;
+
+typedef const slgpu_plugin_v1* (*slgpu_plugin_entry_fn)(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

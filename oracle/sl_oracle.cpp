@@ -352,22 +352,20 @@ struct Regression {
 /* ------------------------------------------------------------------------------------------------
  * ProposalShaper -- src/infer/adaptive.cpp:155-209.  Dense row-major d x d, lower triangle used.
  * Frobenius norm: R.norm() (adaptive.cpp:200).  Eigen's summation order is not pinned by any
- * reference test; the canonical order here (and in the kernels) is: slot l<32 sums, with fma, the
- * squares of rows l, l+32, ... each left to right; then a 5-stage butterfly over the 32 slots.
+ * reference test; the canonical order here (and in the kernels) is: every row r sums the squares of
+ * its lower-triangle entries left to right with fma (starting from 0); slot l<32 adds the row sums of
+ * rows l, l+32, ... in that order; then a halving tree 16,8,4,2,1 over the 32 slots.
  * ---------------------------------------------------------------------------------------------- */
 double frobenius_lower(const double* L, u32 d) {
   double slot[32];
-  for (u32 l = 0; l < 32; ++l) {
+  for (u32 l = 0; l < 32; ++l) slot[l] = 0.0;
+  for (u32 r = 0; r < d; ++r) {
     double acc = 0.0;
-    for (u32 r = l; r < d; r += 32)
-      for (u32 k = 0; k <= r; ++k) acc = std::fma(L[(size_t)r * d + k], L[(size_t)r * d + k], acc);
-    slot[l] = acc;
+    for (u32 k = 0; k <= r; ++k) acc = std::fma(L[(size_t)r * d + k], L[(size_t)r * d + k], acc);
+    slot[r & 31u] += acc;
   }
-  for (u32 m = 16; m > 0; m >>= 1) {
-    double t[32];
-    for (u32 l = 0; l < 32; ++l) t[l] = slot[l] + slot[l ^ m];
-    std::memcpy(slot, t, sizeof t);
-  }
+  for (u32 m = 16; m > 0; m >>= 1)
+    for (u32 l = 0; l < m; ++l) slot[l] += slot[l + m];
   return std::sqrt(slot[0]);
 }
 

@@ -1,0 +1,1002 @@
+// engine.cu -- host side of the B200 parallel-tempering engine behind include/slgpu.h.
+//
+// Replaces, for the GPU path, the construction / initialisation / main-loop half of
+// runSampler (src/app/serverwrapper.cpp:44-138) and the ChainArray -> CSVChainArrayWriter sink
+// (src/infer/chainarray.cpp:109-155, src/db/db.cpp:27-47).  The step loop itself is the plugin-instantiated
+// kernels of include/slgpu_device.cuh; the tier models are csrc/tier_kernels.cuh.
+//
+// Launch schedule ("batched" schedule): the tier models are frozen between adapt points.
+// Round r (0-based) makes the chain length r+2; a swap sweep happens when (r+2) % swapInterval == 0 and
+// an adapt point follows the round with (r+2) % adaptInterval == 0.  step_rounds() cuts the requested
+// rounds into launches that end at adapt points (or after maxRoundsPerLaunch rounds), each followed,
+// at an adapt point, by k_tier_adapt + k_ladder.  Cold-chain rows of a launch land in one of kSegments
+// device segment buffers; with sink "host"/"csv" a second stream copies each finished segment into a
+// pinned host ring while the next launch runs.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "json_min.hpp"
+#include "slgpu.h"
+#include "slgpu_plugin.h"
+#include "tier_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+slgpu_status fail(slgpu_status st, const std::string& msg) {
+  g_err = msg;
+  return st;
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t cu_try_err = (expr);                                                         \
+    if (cu_try_err != cudaSuccess)                                                           \
+      return fail(SLGPU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(cu_try_err)); \
+  } while (0)
+
+constexpr int kSegments = 3;
+enum Sink { SINK_NONE, SINK_DEVICE, SINK_HOST, SINK_CSV };
+
+struct Settings {
+  // src/app/serverwrapper.hpp:64-91
+  uint32_t nStacks = 0, nTemps = 0, swapInterval = 0, nJobTypes = 0, nDims = 0;
+  uint64_t nSamplesTotal = 0;
+  double loggingRateSec = 0, optimalAcceptRate = 0, optimalSwapRate = 0;
+  std::string outputPath;
+  bool useInitial = false;
+  std::vector<double> initial, mn, mx;
+  // "gpu" block
+  int device = 0;
+  uint64_t seed = 1234;
+  uint32_t stackOffset = 0;
+  int rng = SLGPU_RNG_PHILOX;
+  Sink sink = SINK_DEVICE;
+  uint32_t adaptInterval = 0, maxRoundsPerLaunch = 64;
+  uint64_t hostRingRounds = 0;
+  bool overwrite = false;
+};
+
+struct Segment {
+  double* dev = nullptr;
+  cudaEvent_t written = nullptr, copied = nullptr;
+  bool copy_pending = false;
+};
+
+struct PendingCopy {
+  cudaEvent_t ev;
+  uint64_t rows_end;
+};
+
+}  // namespace
+
+struct slgpu_engine {
+  Settings cfg;
+  void* dl = nullptr;
+  const slgpu_plugin_v1* plug = nullptr;
+  cudaStream_t compute = nullptr, drain = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  std::vector<void*> allocs;
+  slgpu_step_params P{};
+  double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr;
+  void* d_payload = nullptr;
+  double *d_rp_z = nullptr, *d_rp_umh = nullptr, *d_rp_uswap = nullptr, *d_rp_xinit = nullptr;
+  bool initialised = false, failed = false;
+  uint64_t rounds_done = 0, launches = 0, rows_emitted = 0;
+  uint32_t seg_rounds = 0, row_w = 0;
+  size_t C = 0;
+  Segment seg[kSegments];
+  uint64_t seg_next = 0;
+  // host ring (sink host / csv)
+  double* ring = nullptr;
+  size_t ring_rows = 0;
+  uint64_t rows_enq = 0, rows_landed = 0, rows_consumed = 0;
+  std::deque<PendingCopy> pending;
+  std::vector<cudaEvent_t> ev_pool;
+  // csv sink
+  std::vector<std::string> csv_buf;
+  size_t csv_buffered = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------- config
+// readSettings<T> semantics (src/app/jsonsettings.hpp:22-35): a missing or mistyped key is fatal.
+struct ConfigError {
+  std::string msg;
+};
+
+const slgpu_json::Value& need(const slgpu_json::Value& j, const char* key, slgpu_json::Value::Kind kind) {
+  const slgpu_json::Value* v = j.find(key);
+  if (!v || v->kind != kind) throw ConfigError{std::string(key) + " not found in config file and no default value exists."};
+  return *v;
+}
+double need_num(const slgpu_json::Value& j, const char* key) { return need(j, key, slgpu_json::Value::Number).num; }
+uint64_t need_uint(const slgpu_json::Value& j, const char* key) {
+  const double v = need_num(j, key);
+  if (!(v >= 0.0) || v != std::floor(v) || v > 1.8e19) throw ConfigError{std::string(key) + " must be a non-negative integer."};
+  return (uint64_t)v;
+}
+std::vector<double> need_vec(const slgpu_json::Value& j, const char* key) {
+  const slgpu_json::Value& a = need(j, key, slgpu_json::Value::Array);
+  std::vector<double> out;
+  for (const auto& e : a.arr) {
+    if (e.kind != slgpu_json::Value::Number) throw ConfigError{std::string(key) + " must be an array of numbers."};
+    out.push_back(e.num);
+  }
+  return out;
+}
+
+Settings parse_settings(const char* text) {
+  slgpu_json::Value j;
+  try {
+    j = slgpu_json::parse(text);
+  } catch (const std::exception& ex) {
+    throw ConfigError{ex.what()};
+  }
+  if (j.kind != slgpu_json::Value::Object) throw ConfigError{"config must be a JSON object"};
+  Settings s;
+  s.nStacks = (uint32_t)need_uint(j, "nStacks");
+  s.nTemps = (uint32_t)need_uint(j, "nTemperatures");
+  s.nSamplesTotal = need_uint(j, "nSamplesTotal");
+  s.swapInterval = (uint32_t)need_uint(j, "swapInterval");
+  s.loggingRateSec = need_num(j, "loggingRateSec");
+  s.nJobTypes = (uint32_t)need_uint(j, "nJobTypes");
+  s.outputPath = need(j, "outputPath", slgpu_json::Value::String).str;
+  s.optimalAcceptRate = need_num(j, "optimalAcceptRate");
+  s.optimalSwapRate = need_num(j, "optimalSwapRate");
+  s.useInitial = need(j, "useInitial", slgpu_json::Value::Bool).b;
+  if (s.useInitial) s.initial = need_vec(j, "initial");
+  s.mn = need_vec(j, "min");
+  s.mx = need_vec(j, "max");
+  // ProposalBoundsFromJSON, src/infer/sampler.hpp:34-60
+  if (s.mn.size() != s.mx.size())
+    throw ConfigError{"Proposal bounds dimension mismatch: nMin=" + std::to_string(s.mn.size()) + ", nMax=" + std::to_string(s.mx.size())};
+  s.nDims = (uint32_t)s.mn.size();
+  if (s.useInitial && s.initial.size() != s.nDims) throw ConfigError{"initial has the wrong number of dimensions"};
+  if (s.nDims == 0 || s.nDims > SLGPU_MAX_DIMS) throw ConfigError{"nDims must be in 1.." + std::to_string(SLGPU_MAX_DIMS)};
+  if (s.nStacks == 0) throw ConfigError{"nStacks must be positive"};
+  if (s.nTemps == 0 || s.nTemps > SLGPU_MAX_TEMPS) throw ConfigError{"nTemperatures must be in 1.." + std::to_string(SLGPU_MAX_TEMPS)};
+  if (s.swapInterval == 0) throw ConfigError{"swapInterval must be positive"};
+  if (s.nJobTypes == 0) throw ConfigError{"nJobTypes must be positive"};
+  for (uint32_t i = 0; i < s.nDims; ++i)
+    if (!(s.mx[i] > s.mn[i])) throw ConfigError{"max must exceed min in every dimension"};
+  s.adaptInterval = s.swapInterval;
+  if (const slgpu_json::Value* g = j.find("gpu")) {
+    if (g->kind != slgpu_json::Value::Object) throw ConfigError{"gpu must be an object"};
+    if (g->find("device")) s.device = (int)need_uint(*g, "device");
+    if (g->find("seed")) s.seed = need_uint(*g, "seed");
+    if (g->find("stackOffset")) s.stackOffset = (uint32_t)need_uint(*g, "stackOffset");
+    if (g->find("adaptInterval")) s.adaptInterval = (uint32_t)need_uint(*g, "adaptInterval");
+    if (g->find("maxRoundsPerLaunch")) s.maxRoundsPerLaunch = (uint32_t)need_uint(*g, "maxRoundsPerLaunch");
+    if (g->find("hostRingRounds")) s.hostRingRounds = need_uint(*g, "hostRingRounds");
+    if (g->find("overwrite")) s.overwrite = need(*g, "overwrite", slgpu_json::Value::Bool).b;
+    if (g->find("rng")) {
+      const std::string& r = need(*g, "rng", slgpu_json::Value::String).str;
+      if (r == "philox") s.rng = SLGPU_RNG_PHILOX;
+      else if (r == "replay") s.rng = SLGPU_RNG_REPLAY;
+      else throw ConfigError{"gpu.rng must be \"philox\" or \"replay\""};
+    }
+    if (g->find("sink")) {
+      const std::string& k = need(*g, "sink", slgpu_json::Value::String).str;
+      if (k == "none") s.sink = SINK_NONE;
+      else if (k == "device") s.sink = SINK_DEVICE;
+      else if (k == "host") s.sink = SINK_HOST;
+      else if (k == "csv") s.sink = SINK_CSV;
+      else throw ConfigError{"gpu.sink must be one of none, device, host, csv"};
+    }
+  }
+  if (s.adaptInterval == 0 || s.maxRoundsPerLaunch == 0) throw ConfigError{"gpu.adaptInterval and gpu.maxRoundsPerLaunch must be positive"};
+  return s;
+}
+
+template <class T>
+slgpu_status dev_alloc(slgpu_engine* e, T** out, size_t n) {
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  e->allocs.push_back(p);
+  *out = (T*)p;
+  return SLGPU_OK;
+}
+
+slgpu_status upload(double* dst, const std::vector<double>& v) {
+  CU_TRY(cudaMemcpy(dst, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return SLGPU_OK;
+}
+
+slgpu_status check_ready(slgpu_engine* e, bool need_init) {
+  if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
+  if (e->failed) return fail(SLGPU_E_STATE, "engine is in a failed state: " + g_err);
+  if (need_init && !e->initialised) return fail(SLGPU_E_STATE, "chains are not initialised (call slgpu_init_chains)");
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  return SLGPU_OK;
+}
+
+cudaEvent_t get_event(slgpu_engine* e) {
+  if (!e->ev_pool.empty()) {
+    cudaEvent_t ev = e->ev_pool.back();
+    e->ev_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  return ev;
+}
+
+// rows whose D2H copy has completed
+void poll_landed(slgpu_engine* e, bool block) {
+  while (!e->pending.empty()) {
+    PendingCopy& pc = e->pending.front();
+    if (block) cudaEventSynchronize(pc.ev);
+    else if (cudaEventQuery(pc.ev) != cudaSuccess) break;
+    e->rows_landed = pc.rows_end;
+    e->ev_pool.push_back(pc.ev);
+    e->pending.pop_front();
+  }
+  if (e->cfg.overwrite && e->rows_landed > e->ring_rows && e->rows_consumed + e->ring_rows < e->rows_landed)
+    e->rows_consumed = e->rows_landed - e->ring_rows;
+}
+
+size_t format_row(const double* row, uint32_t d, char* out, size_t cap) {
+  // operator<<(ostream&, State), src/db/db.cpp:18-25: default ostream formatting == "%g"
+  std::string s;
+  char buf[64];
+  for (uint32_t i = 0; i < d; ++i) {
+    std::snprintf(buf, sizeof buf, "%g,", row[i]);
+    s += buf;
+  }
+  std::snprintf(buf, sizeof buf, "%g,%g,%g,%d,%d", row[d], row[d + 1], row[d + 2], (int)row[d + 3], (int)row[d + 4]);
+  s += buf;
+  if (out && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(out, s.data(), n);
+    out[n] = 0;
+  }
+  return s.size();
+}
+
+std::string csv_path(const slgpu_engine* e, uint32_t local_stack) {
+  return e->cfg.outputPath + "/" + std::to_string(e->cfg.stackOffset + local_stack) + ".csv";
+}
+
+slgpu_status csv_flush_files(slgpu_engine* e) {
+  for (uint32_t s = 0; s < e->cfg.nStacks; ++s) {
+    if (e->csv_buf[s].empty()) continue;
+    std::ofstream f(csv_path(e, s), std::ios::app | std::ios::binary);
+    if (!f.good()) return fail(SLGPU_E_IO, "cannot append to " + csv_path(e, s));
+    f.write(e->csv_buf[s].data(), (std::streamsize)e->csv_buf[s].size());
+    e->csv_buf[s].clear();
+  }
+  e->csv_buffered = 0;
+  return SLGPU_OK;
+}
+
+// format every landed row into the per-stack buffers (one <outputPath>/<stack>.csv per stack, db.cpp:27-35)
+slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
+  poll_landed(e, block);
+  char line[64 * (SLGPU_MAX_DIMS + 8)];
+  const uint32_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  while (e->rows_consumed < e->rows_landed) {
+    const uint64_t r = e->rows_consumed;
+    const double* row = e->ring + (size_t)(r % e->ring_rows) * e->row_w;
+    const size_t n = format_row(row, d, line, sizeof line);
+    std::string& b = e->csv_buf[(size_t)(r % S)];
+    b.append(line, n);
+    b.push_back('\n');
+    e->csv_buffered += n + 1;
+    e->rows_consumed++;
+  }
+  if (finalise || e->csv_buffered > (64u << 20)) return csv_flush_files(e);
+  return SLGPU_OK;
+}
+
+// queue the D2H copy of a finished segment into the host ring
+slgpu_status enqueue_copy(slgpu_engine* e, Segment& sg, uint64_t n_rows) {
+  CU_TRY(cudaStreamWaitEvent(e->drain, sg.written, 0));
+  uint64_t done = 0;
+  while (done < n_rows) {
+    const size_t pos = (size_t)((e->rows_enq + done) % e->ring_rows);
+    const uint64_t n = std::min<uint64_t>(n_rows - done, e->ring_rows - pos);
+    CU_TRY(cudaMemcpyAsync(e->ring + pos * e->row_w, sg.dev + (size_t)done * e->row_w, (size_t)n * e->row_w * sizeof(double),
+                           cudaMemcpyDeviceToHost, e->drain));
+    done += n;
+  }
+  CU_TRY(cudaEventRecord(sg.copied, e->drain));
+  sg.copy_pending = true;
+  cudaEvent_t ev = get_event(e);
+  CU_TRY(cudaEventRecord(ev, e->drain));
+  e->rows_enq += n_rows;
+  e->pending.push_back({ev, e->rows_enq});
+  return SLGPU_OK;
+}
+
+bool ring_has_room(slgpu_engine* e, uint64_t n_rows) {
+  if (e->cfg.overwrite) return true;
+  return e->rows_enq + n_rows - e->rows_consumed <= e->ring_rows;
+}
+
+// one launch of the plugin's step kernel over [rounds_done, rounds_done + n)
+slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
+  const bool emit = e->cfg.sink != SINK_NONE;
+  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV;
+  const uint64_t n_rows = (uint64_t)n * e->cfg.nStacks;
+  Segment& sg = e->seg[e->seg_next % kSegments];
+  if (emit) {
+    if (to_host) {
+      if (e->cfg.sink == SINK_CSV) {
+        slgpu_status st = csv_pump(e, false, false);
+        if (st != SLGPU_OK) return st;
+        while (!ring_has_room(e, n_rows)) {
+          st = csv_pump(e, true, false);
+          if (st != SLGPU_OK) return st;
+        }
+      }
+      if (sg.copy_pending) CU_TRY(cudaStreamWaitEvent(e->compute, sg.copied, 0));
+    }
+    e->P.rows_out = sg.dev;
+  } else {
+    e->P.rows_out = nullptr;
+  }
+  e->P.round_begin = e->rounds_done;
+  e->P.n_rounds = n;
+  const int rc = e->plug->launch_step(&e->P, (void*)e->compute);
+  if (rc != 0) {
+    e->failed = true;
+    return fail(SLGPU_E_CUDA, std::string("launch_step: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+  e->launches++;
+  if (emit) {
+    e->rows_emitted += n_rows;
+    if (to_host) {
+      CU_TRY(cudaEventRecord(sg.written, e->compute));
+      slgpu_status st = enqueue_copy(e, sg, n_rows);
+      if (st != SLGPU_OK) return st;
+    }
+    e->seg_next++;
+  }
+  e->rounds_done += n;
+  return SLGPU_OK;
+}
+
+slgpu_status adapt_point(slgpu_engine* e) {
+  const uint32_t T = e->cfg.nTemps;
+  slgpu_tier::k_tier_adapt<<<dim3(T, 2), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_models, e->d_sig_w);
+  slgpu_tier::k_ladder<<<1, 32, 0, e->compute>>>(e->d_models, T, e->cfg.optimalSwapRate, e->d_ladder);
+  CU_TRY(cudaGetLastError());
+  e->launches += 2;
+  return SLGPU_OK;
+}
+
+template <class T>
+slgpu_status fetch(std::vector<T>& host, const T* dev, size_t n) {
+  host.resize(n);
+  CU_TRY(cudaMemcpy(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+  return SLGPU_OK;
+}
+
+slgpu_status sync_all(slgpu_engine* e) {
+  cudaError_t a = cudaStreamSynchronize(e->compute);
+  cudaError_t b = cudaStreamSynchronize(e->drain);
+  if (a != cudaSuccess || b != cudaSuccess) {
+    e->failed = true;
+    return fail(SLGPU_E_CUDA, std::string("stream synchronize: ") + cudaGetErrorString(a != cudaSuccess ? a : b));
+  }
+  poll_landed(e, true);
+  return SLGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* slgpu_last_error(void) { return g_err.c_str(); }
+const char* slgpu_version(void) { return "slgpu 0.1 sm_100a"; }
+
+slgpu_status slgpu_create(const char* config_json, const char* plugin_path, const char* plugin_entry, const void* payload,
+                          size_t payload_bytes, slgpu_engine** out) {
+  if (!config_json || !plugin_path || !out) return fail(SLGPU_E_ARG, "config_json, plugin_path and out must not be NULL");
+  *out = nullptr;
+  Settings cfg;
+  try {
+    cfg = parse_settings(config_json);
+  } catch (const ConfigError& ce) {
+    return fail(SLGPU_E_CONFIG, ce.msg);
+  }
+  // plugin
+  void* dl = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return fail(SLGPU_E_PLUGIN, std::string("dlopen: ") + dlerror());
+  const char* sym = plugin_entry && plugin_entry[0] ? plugin_entry : "slgpu_plugin_entry";
+  slgpu_plugin_entry_fn entry = (slgpu_plugin_entry_fn)dlsym(dl, sym);
+  if (!entry) {
+    dlclose(dl);
+    return fail(SLGPU_E_PLUGIN, std::string("plugin has no symbol ") + sym);
+  }
+  const slgpu_plugin_v1* plug = entry();
+  if (!plug || plug->abi_version != SLGPU_PLUGIN_ABI || !plug->launch_init || !plug->launch_step) {
+    dlclose(dl);
+    return fail(SLGPU_E_PLUGIN, "plugin ABI mismatch");
+  }
+  if ((plug->n_job_types && plug->n_job_types != cfg.nJobTypes) || (plug->n_dims && plug->n_dims != cfg.nDims) ||
+      (plug->payload_bytes && plug->payload_bytes != payload_bytes)) {
+    dlclose(dl);
+    return fail(SLGPU_E_PLUGIN, std::string("plugin ") + plug->name + " does not match nJobTypes / dimensions / payload size of the config");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    dlclose(dl);
+    return fail(SLGPU_E_CUDA, "no CUDA device: the engine has no CPU fallback");
+  }
+  if (cfg.device >= ndev) {
+    dlclose(dl);
+    return fail(SLGPU_E_CONFIG, "gpu.device out of range");
+  }
+  slgpu_engine* e = new slgpu_engine();
+  e->cfg = cfg;
+  e->dl = dl;
+  e->plug = plug;
+  slgpu_status st = [&]() -> slgpu_status {
+    CU_TRY(cudaSetDevice(cfg.device));
+    CU_TRY(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&e->drain, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&e->t0));
+    CU_TRY(cudaEventCreate(&e->t1));
+    const uint32_t S = cfg.nStacks, T = cfg.nTemps, d = cfg.nDims;
+    const size_t C = (size_t)S * T;
+    e->C = C;
+    e->row_w = d + SLGPU_ROW_EXTRA;
+    slgpu_step_params& P = e->P;
+    P.n_stacks = S; P.n_temps = T; P.n_dims = d; P.n_job_types = cfg.nJobTypes;
+    P.swap_interval = cfg.swapInterval;
+    P.stack_offset = cfg.stackOffset;
+    P.rng_mode = cfg.rng;
+    P.seed = cfg.seed;
+    P.opt_accept = cfg.optimalAcceptRate;
+    P.sh_count0 = 1000.0;  // src/app/serverwrapper.cpp:50
+    // ProposalShaper ctor, adaptive.cpp:161-164
+    std::vector<double> range(d), n0(d);
+    double n2 = 0.0;
+    for (uint32_t i = 0; i < d; ++i) {
+      range[i] = (cfg.mx[i] - cfg.mn[i]) / 4.0;
+      n2 += range[i] * range[i];
+    }
+    P.prop_norm = std::sqrt(n2);
+    for (uint32_t i = 0; i < d; ++i) n0[i] = range[i] / P.prop_norm;
+    double *d_mn, *d_mx, *d_n0, *d_init = nullptr;
+    slgpu_status s2;
+#define TRY_ST(x) if ((s2 = (x)) != SLGPU_OK) return s2
+    TRY_ST(dev_alloc(e, &d_mn, d)); TRY_ST(upload(d_mn, cfg.mn));
+    TRY_ST(dev_alloc(e, &d_mx, d)); TRY_ST(upload(d_mx, cfg.mx));
+    TRY_ST(dev_alloc(e, &d_n0, d)); TRY_ST(upload(d_n0, n0));
+    if (cfg.useInitial) { TRY_ST(dev_alloc(e, &d_init, d)); TRY_ST(upload(d_init, cfg.initial)); }
+    P.mn = d_mn; P.mx = d_mx; P.n0_diag = d_n0; P.initial = d_init;
+    const size_t nL = (size_t)d * (d + 1) / 2;
+    TRY_ST(dev_alloc(e, &P.x, d * C));
+    TRY_ST(dev_alloc(e, &P.L, nL * C));
+    TRY_ST(dev_alloc(e, &P.energy, C)); TRY_ST(dev_alloc(e, &P.row_sigma, C)); TRY_ST(dev_alloc(e, &P.row_beta, C));
+    TRY_ST(dev_alloc(e, &P.sigma, C)); TRY_ST(dev_alloc(e, &P.beta, C)); TRY_ST(dev_alloc(e, &P.nscale, C));
+    TRY_ST(dev_alloc(e, &P.sh_count, C));
+    TRY_ST(dev_alloc(e, &P.accepted, C)); TRY_ST(dev_alloc(e, &P.swap_type, C));
+    TRY_ST(dev_alloc(e, &P.lg_accepts, C)); TRY_ST(dev_alloc(e, &P.lg_swaps, C)); TRY_ST(dev_alloc(e, &P.lg_swap_attempts, C));
+    TRY_ST(dev_alloc(e, &P.lg_min_energy, C));
+    TRY_ST(dev_alloc(e, &P.p_sig, 9 * C)); TRY_ST(dev_alloc(e, &P.p_beta, 9 * C));
+    TRY_ST(dev_alloc(e, &P.ep_m, (size_t)d * S)); TRY_ST(dev_alloc(e, &P.ep_s, (size_t)d * S));
+    TRY_ST(dev_alloc(e, &e->d_models, (size_t)2 * T * slgpu_tier::kModelStride));
+    TRY_ST(dev_alloc(e, &e->d_sig_w, (size_t)3 * T));
+    TRY_ST(dev_alloc(e, &e->d_ladder, T));
+    P.sig_w = e->d_sig_w;
+    P.ladder = e->d_ladder;
+    if (payload && payload_bytes) {
+      TRY_ST(dev_alloc(e, (char**)&e->d_payload, payload_bytes));
+      CU_TRY(cudaMemcpy(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice));
+    }
+    P.payload = e->d_payload;
+    // sink
+    e->seg_rounds = std::min(cfg.adaptInterval, cfg.maxRoundsPerLaunch);
+    if (cfg.sink != SINK_NONE) {
+      const size_t seg_doubles = (size_t)e->seg_rounds * S * e->row_w;
+      const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;
+      for (int i = 0; i < kSegments; ++i) {
+        if (i < nseg) TRY_ST(dev_alloc(e, &e->seg[i].dev, seg_doubles));
+        else e->seg[i].dev = e->seg[0].dev;
+        CU_TRY(cudaEventCreateWithFlags(&e->seg[i].written, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&e->seg[i].copied, cudaEventDisableTiming));
+      }
+    }
+    if (cfg.sink == SINK_HOST || cfg.sink == SINK_CSV) {
+      uint64_t rr = cfg.hostRingRounds ? cfg.hostRingRounds : (uint64_t)8 * e->seg_rounds;
+      rr = std::max<uint64_t>(rr, (uint64_t)e->seg_rounds + 1);
+      e->ring_rows = (size_t)rr * S;
+      CU_TRY(cudaHostAlloc((void**)&e->ring, e->ring_rows * e->row_w * sizeof(double), cudaHostAllocDefault));
+    }
+    if (cfg.sink == SINK_CSV) {
+      // CSVChainArrayWriter ctor, db.cpp:27-35: one file per stack, truncated on open
+      mkdir(cfg.outputPath.c_str(), 0777);
+      e->csv_buf.assign(S, std::string());
+      for (uint32_t s = 0; s < S; ++s) {
+        std::ofstream f(csv_path(e, s), std::ios::trunc);
+        if (!f.good()) return fail(SLGPU_E_IO, "cannot create " + csv_path(e, s));
+      }
+    }
+    slgpu_tier::k_tier_init<<<1, 32, 0, e->compute>>>(e->d_models, e->d_sig_w, e->d_ladder, T, cfg.optimalSwapRate);
+    CU_TRY(cudaGetLastError());
+    e->launches++;
+    CU_TRY(cudaStreamSynchronize(e->compute));
+#undef TRY_ST
+    return SLGPU_OK;
+  }();
+  if (st != SLGPU_OK) {
+    const std::string keep = g_err;
+    slgpu_destroy(e);
+    g_err = keep;
+    return st;
+  }
+  *out = e;
+  return SLGPU_OK;
+}
+
+void slgpu_destroy(slgpu_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->compute) cudaStreamSynchronize(e->compute);
+  if (e->drain) cudaStreamSynchronize(e->drain);
+  for (void* p : e->allocs) cudaFree(p);
+  for (auto& p : {e->d_rp_z, e->d_rp_umh, e->d_rp_uswap, e->d_rp_xinit})
+    if (p) cudaFree(p);
+  if (e->ring) cudaFreeHost(e->ring);
+  for (auto& sg : e->seg) {
+    if (sg.written) cudaEventDestroy(sg.written);
+    if (sg.copied) cudaEventDestroy(sg.copied);
+  }
+  for (auto& pc : e->pending) cudaEventDestroy(pc.ev);
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->t0) cudaEventDestroy(e->t0);
+  if (e->t1) cudaEventDestroy(e->t1);
+  if (e->compute) cudaStreamDestroy(e->compute);
+  if (e->drain) cudaStreamDestroy(e->drain);
+  if (e->dl) dlclose(e->dl);
+  delete e;
+}
+
+slgpu_status slgpu_set_replay(slgpu_engine* e, const double* z, const double* u_mh, const double* u_swap, const double* x_init,
+                              uint64_t n_rounds) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (e->cfg.rng != SLGPU_RNG_REPLAY) return fail(SLGPU_E_STATE, "gpu.rng is not \"replay\"");
+  if (!z || !u_mh || !u_swap || (!x_init && !e->cfg.useInitial)) return fail(SLGPU_E_ARG, "replay buffers must not be NULL");
+  st = sync_all(e);
+  if (st != SLGPU_OK) return st;
+  for (double** p : {&e->d_rp_z, &e->d_rp_umh, &e->d_rp_uswap, &e->d_rp_xinit}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  const size_t C = e->C, d = e->cfg.nDims;
+  auto up = [&](double** dst, const double* src, size_t n) -> slgpu_status {
+    CU_TRY(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(double)));
+    if (n) CU_TRY(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+    return SLGPU_OK;
+  };
+  if ((st = up(&e->d_rp_z, z, (size_t)n_rounds * C * d)) != SLGPU_OK) return st;
+  if ((st = up(&e->d_rp_umh, u_mh, (size_t)n_rounds * C)) != SLGPU_OK) return st;
+  if ((st = up(&e->d_rp_uswap, u_swap, (size_t)n_rounds * C)) != SLGPU_OK) return st;
+  if (x_init && (st = up(&e->d_rp_xinit, x_init, C * d)) != SLGPU_OK) return st;
+  e->P.rp_z = e->d_rp_z; e->P.rp_umh = e->d_rp_umh; e->P.rp_uswap = e->d_rp_uswap; e->P.rp_xinit = e->d_rp_xinit;
+  e->P.replay_rounds = n_rounds;
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_init_chains(slgpu_engine* e) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (e->initialised) return fail(SLGPU_E_STATE, "chains are already initialised");
+  if (e->cfg.rng == SLGPU_RNG_REPLAY && !e->cfg.useInitial && !e->d_rp_xinit)
+    return fail(SLGPU_E_STATE, "rng \"replay\" needs slgpu_set_replay before slgpu_init_chains");
+  const bool emit = e->cfg.sink != SINK_NONE;
+  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV;
+  Segment& sg = e->seg[e->seg_next % kSegments];
+  e->P.rows_out = emit ? sg.dev : nullptr;
+  e->P.round_begin = 0;
+  e->P.n_rounds = 0;
+  const int rc = e->plug->launch_init(&e->P, (void*)e->compute);
+  if (rc != 0) {
+    e->failed = true;
+    return fail(SLGPU_E_CUDA, std::string("launch_init: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+  e->launches++;
+  if (emit) {
+    e->rows_emitted += e->cfg.nStacks;
+    if (to_host) {
+      CU_TRY(cudaEventRecord(sg.written, e->compute));
+      if ((st = enqueue_copy(e, sg, e->cfg.nStacks)) != SLGPU_OK) return st;
+    }
+    e->seg_next++;
+  }
+  e->initialised = true;
+  e->rounds_done = 0;
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (e->cfg.rng == SLGPU_RNG_REPLAY && e->rounds_done + n_rounds > e->P.replay_rounds)
+    return fail(SLGPU_E_ARG, "not enough recorded rounds in the replay buffers");
+  if (e->cfg.sink == SINK_HOST) {
+    poll_landed(e, false);
+    if (!ring_has_room(e, n_rounds * e->cfg.nStacks)) {
+      poll_landed(e, true);
+      if (!ring_has_room(e, n_rounds * e->cfg.nStacks))
+        return fail(SLGPU_E_FULL, "host ring cannot take the rows of the requested rounds: drain first or raise gpu.hostRingRounds");
+    }
+  }
+  const uint64_t A = e->cfg.adaptInterval;
+  uint64_t left = n_rounds;
+  while (left) {
+    const uint64_t r = e->rounds_done;
+    const uint64_t to_adapt = (A - (r + 2) % A) % A + 1;  // rounds up to and including the next adapt round
+    const uint32_t n = (uint32_t)std::min<uint64_t>({left, to_adapt, (uint64_t)e->seg_rounds});
+    if ((st = launch_rounds(e, n)) != SLGPU_OK) return st;
+    if ((e->rounds_done + 1) % A == 0 && (st = adapt_point(e)) != SLGPU_OK) return st;
+    left -= n;
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_sync(slgpu_engine* e) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  return sync_all(e);
+}
+
+slgpu_status slgpu_run(slgpu_engine* e) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!e->initialised && (st = slgpu_init_chains(e)) != SLGPU_OK) return st;
+  // stop rule, src/app/serverwrapper.cpp:100-107: count cold-chain steps over all stacks
+  const uint64_t S = e->cfg.nStacks;
+  const uint64_t total = (e->cfg.nSamplesTotal + S - 1) / S;
+  while (e->rounds_done < total) {
+    uint64_t n = std::min<uint64_t>(total - e->rounds_done, (uint64_t)e->seg_rounds * 4);
+    if (e->cfg.sink == SINK_HOST && !e->cfg.overwrite) {
+      poll_landed(e, false);
+      const uint64_t room = (e->ring_rows - (e->rows_enq - e->rows_consumed)) / S;
+      if (room == 0) return fail(SLGPU_E_FULL, "host ring is full: slgpu_run with sink \"host\" needs gpu.overwrite or a ring that holds the run");
+      n = std::min(n, room);
+    }
+    if ((st = slgpu_step_rounds(e, n)) != SLGPU_OK) return st;
+  }
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  if (e->cfg.sink == SINK_CSV) return csv_pump(e, true, true);  // Sampler::flush, sampler.cpp:216-235
+  return SLGPU_OK;
+}
+
+uint64_t slgpu_rounds_done(const slgpu_engine* e) { return e ? e->rounds_done : 0; }
+uint64_t slgpu_rows_emitted(const slgpu_engine* e) { return e ? e->rows_emitted : 0; }
+uint64_t slgpu_launch_count(const slgpu_engine* e) { return e ? e->launches : 0; }
+uint32_t slgpu_n_dims(const slgpu_engine* e) { return e ? e->cfg.nDims : 0; }
+uint32_t slgpu_n_chains(const slgpu_engine* e) { return e ? (uint32_t)e->C : 0; }
+
+slgpu_status slgpu_drain(slgpu_engine* e, double* rows, size_t cap_rows, size_t* n_rows) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!n_rows || (!rows && cap_rows)) return fail(SLGPU_E_ARG, "rows / n_rows must not be NULL");
+  if (e->cfg.sink != SINK_HOST) return fail(SLGPU_E_STATE, "slgpu_drain needs gpu.sink \"host\"");
+  poll_landed(e, true);
+  size_t n = (size_t)std::min<uint64_t>(cap_rows, e->rows_landed - e->rows_consumed);
+  size_t done = 0;
+  while (done < n) {
+    const size_t pos = (size_t)((e->rows_consumed + done) % e->ring_rows);
+    const size_t k = std::min(n - done, e->ring_rows - pos);
+    std::memcpy(rows + done * e->row_w, e->ring + pos * e->row_w, k * e->row_w * sizeof(double));
+    done += k;
+  }
+  e->rows_consumed += n;
+  *n_rows = n;
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_peek(slgpu_engine* e, const double** span0, size_t* n0, const double** span1, size_t* n1) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!span0 || !n0 || !span1 || !n1) return fail(SLGPU_E_ARG, "span pointers must not be NULL");
+  if (e->cfg.sink != SINK_HOST) return fail(SLGPU_E_STATE, "slgpu_peek needs gpu.sink \"host\"");
+  poll_landed(e, false);
+  const size_t avail = (size_t)(e->rows_landed - e->rows_consumed);
+  const size_t pos = (size_t)(e->rows_consumed % e->ring_rows);
+  const size_t first = std::min(avail, e->ring_rows - pos);
+  *span0 = e->ring + pos * e->row_w;
+  *n0 = first;
+  *span1 = e->ring;
+  *n1 = avail - first;
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_advance(slgpu_engine* e, size_t n_rows) {
+  if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
+  if (n_rows > e->rows_landed - e->rows_consumed) return fail(SLGPU_E_ARG, "cannot advance past the landed rows");
+  e->rows_consumed += n_rows;
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_timer_start(slgpu_engine* e) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  CU_TRY(cudaEventRecord(e->t0, e->compute));
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_timer_stop(slgpu_engine* e, double* elapsed_ms) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!elapsed_ms) return fail(SLGPU_E_ARG, "elapsed_ms must not be NULL");
+  CU_TRY(cudaEventRecord(e->t1, e->compute));
+  CU_TRY(cudaEventSynchronize(e->t1));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, e->t0, e->t1));
+  *elapsed_ms = ms;
+  return SLGPU_OK;
+}
+
+// ---------------------------------------------------------------- state inspection
+slgpu_status slgpu_get_last_rows(slgpu_engine* e, double* rows) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (!rows) return fail(SLGPU_E_ARG, "rows must not be NULL");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const size_t C = e->C, d = e->cfg.nDims, w = e->row_w;
+  std::vector<double> x, en, rs, rb;
+  std::vector<int32_t> ac, sw;
+  if ((st = fetch(x, e->P.x, d * C)) != SLGPU_OK || (st = fetch(en, e->P.energy, C)) != SLGPU_OK ||
+      (st = fetch(rs, e->P.row_sigma, C)) != SLGPU_OK || (st = fetch(rb, e->P.row_beta, C)) != SLGPU_OK ||
+      (st = fetch(ac, e->P.accepted, C)) != SLGPU_OK || (st = fetch(sw, e->P.swap_type, C)) != SLGPU_OK)
+    return st;
+  for (size_t c = 0; c < C; ++c) {
+    double* r = rows + c * w;
+    for (size_t i = 0; i < d; ++i) r[i] = x[i * C + c];
+    r[d] = en[c]; r[d + 1] = rs[c]; r[d + 2] = rb[c]; r[d + 3] = ac[c]; r[d + 4] = sw[c];
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_get_sigma_beta(slgpu_engine* e, double* sigma, double* beta) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  if (sigma) CU_TRY(cudaMemcpy(sigma, e->P.sigma, e->C * sizeof(double), cudaMemcpyDeviceToHost));
+  if (beta) CU_TRY(cudaMemcpy(beta, e->P.beta, e->C * sizeof(double), cudaMemcpyDeviceToHost));
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double* N, double* count) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (chain >= e->C) return fail(SLGPU_E_ARG, "chain out of range");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const size_t C = e->C, d = e->cfg.nDims, nL = d * (d + 1) / 2;
+  std::vector<double> packed(nL);
+  CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), e->P.L + chain, C * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
+  double cnt = 0.0, ns = 0.0;
+  CU_TRY(cudaMemcpy(&cnt, e->P.sh_count + chain, sizeof(double), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&ns, e->P.nscale + chain, sizeof(double), cudaMemcpyDeviceToHost));
+  if (count) *count = cnt;
+  const bool fresh = (cnt == e->P.sh_count0);
+  for (size_t r = 0; r < d; ++r)
+    for (size_t k = 0; k < d; ++k) {
+      const double l = (k <= r) ? packed[r * (r + 1) / 2 + k] : 0.0;
+      if (L) L[r * d + k] = l;
+      if (N) {
+        double n;
+        if (fresh) n = (r == k) ? ((e->cfg.mx[r] - e->cfg.mn[r]) / 4.0) / e->P.prop_norm : 0.0;
+        else n = (k <= r) ? l * ns + (r == k ? 1e-4 : 0.0) : 0.0;  // adaptive.cpp:200-204
+        N[r * d + k] = n;
+      }
+    }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_get_models(slgpu_engine* e, int which, double* mu_xx, double* mu_xy, double* weight, double* count) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (which != 0 && which != 1) return fail(SLGPU_E_ARG, "which must be 0 (sigma) or 1 (beta)");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const uint32_t T = e->cfg.nTemps;
+  std::vector<double> m;
+  if ((st = fetch(m, e->d_models + (size_t)which * T * slgpu_tier::kModelStride, (size_t)T * slgpu_tier::kModelStride)) != SLGPU_OK) return st;
+  for (uint32_t t = 0; t < T; ++t) {
+    const double* p = m.data() + (size_t)t * slgpu_tier::kModelStride;
+    if (mu_xx) std::memcpy(mu_xx + 9 * t, p, 9 * sizeof(double));
+    if (mu_xy) std::memcpy(mu_xy + 3 * t, p + 9, 3 * sizeof(double));
+    if (weight) std::memcpy(weight + 3 * t, p + 12, 3 * sizeof(double));
+    if (count) count[t] = p[15];
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_get_ladder(slgpu_engine* e, double* ladder) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!ladder) return fail(SLGPU_E_ARG, "ladder must not be NULL");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  CU_TRY(cudaMemcpy(ladder, e->d_ladder, e->cfg.nTemps * sizeof(double), cudaMemcpyDeviceToHost));
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_get_counters(slgpu_engine* e, uint64_t* length, uint64_t* accepts, uint64_t* swaps, uint64_t* swap_attempts,
+                                double* min_energy) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const size_t C = e->C;
+  std::vector<uint32_t> a, s, t;
+  if ((st = fetch(a, e->P.lg_accepts, C)) != SLGPU_OK || (st = fetch(s, e->P.lg_swaps, C)) != SLGPU_OK ||
+      (st = fetch(t, e->P.lg_swap_attempts, C)) != SLGPU_OK)
+    return st;
+  for (size_t c = 0; c < C; ++c) {
+    if (length) length[c] = e->rounds_done + 1;  // TableLogger lengths start at 1 (logging.cpp:29-33)
+    if (accepts) accepts[c] = a[c];
+    if (swaps) swaps[c] = s[c];
+    if (swap_attempts) swap_attempts[c] = t[c];
+  }
+  if (min_energy) CU_TRY(cudaMemcpy(min_energy, e->P.lg_min_energy, C * sizeof(double), cudaMemcpyDeviceToHost));
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_rhat_stage1(slgpu_engine* e, double* sum_m, double* n_stacks, double* n_samples) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (!sum_m || !n_stacks || !n_samples) return fail(SLGPU_E_ARG, "output pointers must not be NULL");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const size_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  std::vector<double> M;
+  if ((st = fetch(M, e->P.ep_m, d * S)) != SLGPU_OK) return st;
+  for (size_t i = 0; i < d; ++i) {
+    double acc = 0.0;
+    for (size_t s = 0; s < S; ++s) acc += M[i * S + s];
+    sum_m[i] = acc;
+  }
+  *n_stacks = (double)S;
+  *n_samples = (double)e->rounds_done;  // every stack has seen the same number of cold rows
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_rhat_stage2(slgpu_engine* e, const double* mean, double* sum_dm2, double* sum_s) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (!mean || !sum_dm2 || !sum_s) return fail(SLGPU_E_ARG, "pointers must not be NULL");
+  const size_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  std::vector<double> M, V;
+  if ((st = fetch(M, e->P.ep_m, d * S)) != SLGPU_OK || (st = fetch(V, e->P.ep_s, d * S)) != SLGPU_OK) return st;
+  for (size_t i = 0; i < d; ++i) {
+    double b = 0.0, w = 0.0;
+    for (size_t s = 0; s < S; ++s) {
+      const double dm = M[i * S + s] - mean[i];
+      b += dm * dm;
+      w += V[i * S + s];
+    }
+    sum_dm2[i] = b;
+    sum_s[i] = w;
+  }
+  return SLGPU_OK;
+}
+
+void slgpu_rhat_finish(const double* sum_dm2, const double* sum_s, double m, double n, uint32_t d, double* rhat) {
+  // diagnostics.cpp:58-70 with B = n/(m-1) sum (M_s - mean)^2, W = (1/m) sum S_s/(n-1)
+  for (uint32_t i = 0; i < d; ++i) {
+    const double b = sum_dm2[i] * (n / (m - 1.0));
+    const double w = (1.0 / m) * sum_s[i] / (n - 1.0);
+    const double vHat = ((n - 1.0) / n) * w + (1.0 / n) * b;
+    rhat[i] = std::sqrt(vHat / (w + 1e-30));
+  }
+}
+
+slgpu_status slgpu_rhat(slgpu_engine* e, double* rhat) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (!rhat) return fail(SLGPU_E_ARG, "rhat must not be NULL");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  // EPSRDiagnostic::rHat, diagnostics.cpp:49-71, in the operation order of the oracle
+  const size_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  std::vector<double> M, V;
+  if ((st = fetch(M, e->P.ep_m, d * S)) != SLGPU_OK || (st = fetch(V, e->P.ep_s, d * S)) != SLGPU_OK) return st;
+  const int nmin = (int)e->rounds_done;
+  const int m = (int)S;
+  for (size_t i = 0; i < d; ++i) {
+    double mean = 0.0;
+    for (size_t s = 0; s < S; ++s) mean += M[i * S + s];
+    mean /= m;
+    double b = 0.0, w = 0.0;
+    for (size_t s = 0; s < S; ++s) {
+      const double dm = M[i * S + s] - mean;
+      b += dm * dm;
+      w += (1.0 / m) * V[i * S + s] / (nmin - 1.0);
+    }
+    b *= nmin / (m - 1.0);
+    const double vHat = ((nmin - 1.0) / nmin) * w + (1.0 / nmin) * b;
+    rhat[i] = std::sqrt(vHat / (w + 1e-30));
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_summary(slgpu_engine* e, char* json, size_t cap, size_t* needed) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  const size_t C = e->C;
+  const uint32_t S = e->cfg.nStacks, T = e->cfg.nTemps, d = e->cfg.nDims;
+  std::vector<uint64_t> len(C), acc(C), sw(C), att(C);
+  std::vector<double> sigma(C), beta(C), rhat(d), ladder(T);
+  if ((st = slgpu_get_counters(e, len.data(), acc.data(), sw.data(), att.data(), nullptr)) != SLGPU_OK) return st;
+  if ((st = slgpu_get_sigma_beta(e, sigma.data(), beta.data())) != SLGPU_OK) return st;
+  if ((st = slgpu_get_ladder(e, ladder.data())) != SLGPU_OK) return st;
+  const bool have_rhat = e->rounds_done >= 2 && S >= 2;
+  if (have_rhat && (st = slgpu_rhat(e, rhat.data())) != SLGPU_OK) return st;
+  std::ostringstream o;
+  o.precision(10);
+  auto tier = [&](const char* name, auto fn) {
+    o << "\"" << name << "\":[";
+    for (uint32_t t = 0; t < T; ++t) {
+      double v = 0.0;
+      for (uint32_t s = 0; s < S; ++s) v += fn((size_t)s * T + t);
+      o << (t ? "," : "") << v / S;
+    }
+    o << "]";
+  };
+  o << "{\"nStacks\":" << S << ",\"nTemperatures\":" << T << ",\"nDims\":" << d << ",\"rounds\":" << e->rounds_done
+    << ",\"rows_emitted\":" << e->rows_emitted << ",\"launches\":" << e->launches << ",";
+  tier("accept_rate", [&](size_t c) { return (double)acc[c] / (double)len[c]; });  // GlbAcptRt, logging.cpp:72
+  o << ",";
+  tier("swap_rate", [&](size_t c) { return (double)sw[c] / (double)att[c]; });  // GlbSwapRt, logging.cpp:75
+  o << ",";
+  tier("sigma", [&](size_t c) { return sigma[c]; });
+  o << ",";
+  tier("beta", [&](size_t c) { return beta[c]; });
+  o << ",\"ladder\":[";
+  for (uint32_t t = 0; t < T; ++t) o << (t ? "," : "") << ladder[t];
+  o << "],\"rhat\":[";
+  if (have_rhat)
+    for (uint32_t i = 0; i < d; ++i) o << (i ? "," : "") << rhat[i];
+  o << "]}";
+  const std::string s = o.str();
+  if (needed) *needed = s.size() + 1;
+  if (json && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(json, s.data(), n);
+    json[n] = 0;
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_points, double* nll) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!x || !nll) return fail(SLGPU_E_ARG, "x and nll must not be NULL");
+  if (!e->plug->launch_eval) return fail(SLGPU_E_PLUGIN, "plugin has no launch_eval");
+  const size_t d = e->cfg.nDims, J = e->cfg.nJobTypes;
+  double *dx = nullptr, *dn = nullptr;
+  CU_TRY(cudaMalloc((void**)&dx, std::max<size_t>(1, n_points * d) * sizeof(double)));
+  CU_TRY(cudaMalloc((void**)&dn, std::max<size_t>(1, n_points * J) * sizeof(double)));
+  cudaError_t err = cudaMemcpy(dx, x, n_points * d * sizeof(double), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = (cudaError_t)e->plug->launch_eval(&e->P, dx, n_points, dn, (void*)e->compute);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->compute);
+  if (err == cudaSuccess) err = cudaMemcpy(nll, dn, n_points * J * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dn);
+  e->launches++;
+  if (err != cudaSuccess) return fail(SLGPU_E_CUDA, std::string("eval: ") + cudaGetErrorString(err));
+  return SLGPU_OK;
+}
+
+size_t slgpu_format_row(const double* row, uint32_t d, char* out, size_t cap) { return format_row(row, d, out, cap); }
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// tier_kernels.cuh -- the per-temperature-tier RegressionAdapter models on the device.
+//
+// Reference: RegressionAdapter (src/infer/adaptive.cpp:27-139).  One 3-feature linear model per tier,
+// shared by every stack, for sigma (caps [-8,4]) and for beta (caps [0,4]) (src/app/serverwrapper.cpp:48-52).
+// The step kernel gathers the sufficient statistics of adaptive.cpp:71-75 per chain; at an adapt point
+// k_tier_adapt sums them over the stacks in a fixed-shape tree (same shape as the oracle's
+// reduce_tree256), folds them into the running means, re-solves the 3x3 system with a column-pivoted
+// Householder QR (adaptive.cpp:78) and rebuilds the beta ladder (computeBetaStack, adaptive.cpp:118-132).
+// Compile with -fmad=false (operation order mirrors oracle/sl_oracle.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slgpu_tier {
+
+constexpr int kModelStride = 16;  // mu_xx[9], mu_xy[3], w[3], count
+constexpr double kInitialCount = 10.0;  // adaptive.cpp:27
+constexpr double kTempVariance = 10.0;  // adaptive.cpp:28
+constexpr double kSigMinCap = -8.0, kSigMaxCap = 4.0, kBetaMinCap = 0.0, kBetaMaxCap = 4.0;  // serverwrapper.cpp:48-49
+
+__device__ inline double smax(double a, double b) { return (a < b) ? b : a; }
+__device__ inline double smin(double a, double b) { return (b < a) ? b : a; }
+
+// colPivHouseholderQr().solve() for a 3x3 system, A row-major (restated from the oracle's qr_solve3)
+__device__ inline void qr_solve3(const double* A, const double* b, double* w) {
+  double M[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) M[r][c] = A[3 * r + c];
+  int perm[3] = {0, 1, 2};
+  double cn[3];
+  for (int c = 0; c < 3; ++c) cn[c] = M[0][c] * M[0][c] + M[1][c] * M[1][c] + M[2][c] * M[2][c];
+  double tau[3] = {0.0, 0.0, 0.0};
+  double cvec[3] = {b[0], b[1], b[2]};
+  double maxpivot = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    int p = k;
+    for (int c = k + 1; c < 3; ++c)
+      if (cn[c] > cn[p]) p = c;
+    if (p != k) {
+      for (int r = 0; r < 3; ++r) { const double tmp = M[r][k]; M[r][k] = M[r][p]; M[r][p] = tmp; }
+      { const double tmp = cn[k]; cn[k] = cn[p]; cn[p] = tmp; }
+      { const int tmp = perm[k]; perm[k] = perm[p]; perm[p] = tmp; }
+    }
+    const double c0 = M[k][k];
+    double tail2 = 0.0;
+    for (int r = k + 1; r < 3; ++r) tail2 += M[r][k] * M[r][k];
+    double beta;
+    if (tail2 == 0.0) {
+      tau[k] = 0.0;
+      beta = c0;
+      for (int r = k + 1; r < 3; ++r) M[r][k] = 0.0;
+    } else {
+      beta = sqrt(c0 * c0 + tail2);
+      if (c0 >= 0.0) beta = -beta;
+      const double den = c0 - beta;
+      for (int r = k + 1; r < 3; ++r) M[r][k] = M[r][k] / den;
+      tau[k] = (beta - c0) / beta;
+    }
+    M[k][k] = beta;
+    if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+    for (int c = k + 1; c < 3; ++c) {
+      double s = M[k][c];
+      for (int r = k + 1; r < 3; ++r) s += M[r][k] * M[r][c];
+      s *= tau[k];
+      M[k][c] -= s;
+      for (int r = k + 1; r < 3; ++r) M[r][c] -= s * M[r][k];
+      cn[c] -= M[k][c] * M[k][c];
+    }
+    {
+      double s = cvec[k];
+      for (int r = k + 1; r < 3; ++r) s += M[r][k] * cvec[r];
+      s *= tau[k];
+      cvec[k] -= s;
+      for (int r = k + 1; r < 3; ++r) cvec[r] -= s * M[r][k];
+    }
+  }
+  const double thresh = 2.220446049250313080847263336181640625e-16 * 3.0 * maxpivot;
+  int rank = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (fabs(M[k][k]) > thresh) ++rank;
+    else break;
+  }
+  double y[3] = {0.0, 0.0, 0.0};
+  for (int i = rank - 1; i >= 0; --i) {
+    double s = cvec[i];
+    for (int c = i + 1; c < rank; ++c) s -= M[i][c] * y[c];
+    y[i] = s / M[i][i];
+  }
+  for (int i = 0; i < 3; ++i) w[perm[i]] = y[i];
+}
+
+// RegressionAdapter ctor, adaptive.cpp:31-61
+__device__ inline void model_init(double* m, double min_cap, double max_cap) {
+  const double rej[3] = {min_cap, 0.0, 1.0};
+  const double acc[3] = {max_cap, 0.0, 1.0};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) m[3 * r + c] = 0.5 * rej[r] * rej[c] + 0.5 * acc[r] * acc[c];
+  m[4] = kTempVariance;
+  for (int r = 0; r < 3; ++r) {
+    m[9 + r] = 0.5 * acc[r];
+    m[12 + r] = m[9 + r];  // weight_ = mu_xy, not solved (adaptive.cpp:57)
+  }
+  m[15] = kInitialCount;
+}
+
+// adaptive.cpp:94-106
+__device__ inline double model_predict(const double* w, double opt, double min_cap, double max_cap, double side) {
+  const double eps = 1e-3;
+  const double denom = smax(eps, w[0]);
+  double numer = -(opt - w[1] * side - w[2]);
+  numer = smax(smin(numer, denom * max_cap), denom * min_cap);
+  return numer / denom;
+}
+
+// running mean of adaptive.cpp:71-75 with alpha = 1/count, applied to N summed samples at once
+__device__ inline void model_update_batched(double* m, const double* P) {
+  const double n = P[5];
+  if (n == 0.0) return;
+  const double c0 = m[15];
+  const double c1 = c0 + n;
+  const double sxx[9] = {P[0], P[1], P[2], P[1], P[3], P[4], P[2], P[4], P[5]};
+  const double sxy[3] = {P[6], P[7], P[8]};
+  for (int i = 0; i < 9; ++i) m[i] = (m[i] * c0 + sxx[i]) / c1;
+  for (int i = 0; i < 3; ++i) m[9 + i] = (m[9 + i] * c0 + sxy[i]) / c1;
+  m[15] = c1;
+  qr_solve3(m, m + 9, m + 12);
+}
+
+// computeBetaStack with the shared models, adaptive.cpp:118-132
+__device__ inline void compute_ladder(const double* beta_models, uint32_t T, double opt_swap, double* ladder) {
+  double logbeta = 0.0;
+  ladder[0] = 1.0;
+  for (uint32_t i = 1; i < T; ++i) {
+    logbeta -= model_predict(beta_models + (size_t)(i - 1) * kModelStride + 12, opt_swap, kBetaMinCap, kBetaMaxCap, logbeta);
+    ladder[i] = exp(logbeta);
+  }
+}
+
+// models: [2][T][kModelStride] (0 sigma, 1 beta); sig_w: [T][3]; ladder: [T]
+__global__ void k_tier_init(double* models, double* sig_w, double* ladder, uint32_t T, double opt_swap) {
+  const uint32_t t = threadIdx.x;
+  if (t < T) {
+    model_init(models + (size_t)t * kModelStride, kSigMinCap, kSigMaxCap);
+    model_init(models + (size_t)(T + t) * kModelStride, kBetaMinCap, kBetaMaxCap);
+    for (int i = 0; i < 3; ++i) sig_w[3 * t + i] = models[(size_t)t * kModelStride + 12 + i];
+  }
+  __syncthreads();
+  if (t == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
+}
+
+// grid (T, 2), 256 threads: block (t, which) sums the 9 statistics of tier t over the stacks, clears
+// them, and folds them into the model.
+__global__ void __launch_bounds__(256) k_tier_adapt(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* models, double* sig_w) {
+  const uint32_t t = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
+  double* P = which ? p_beta : p_sig;
+  const size_t C = (size_t)S * T;
+  __shared__ double a[256];
+  __shared__ double Pk[9];
+  for (int k = 0; k < 9; ++k) {
+    double acc = 0.0;
+    for (uint32_t m = tid; m < S; m += 256) {
+      const size_t idx = (size_t)k * C + (size_t)m * T + t;
+      acc += P[idx];
+      P[idx] = 0.0;
+    }
+    a[tid] = acc;
+    __syncthreads();
+    for (uint32_t s = 128; s > 0; s >>= 1) {
+      if (tid < s) a[tid] += a[tid + s];
+      __syncthreads();
+    }
+    if (tid == 0) Pk[k] = a[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double* m = models + (size_t)(which * T + t) * kModelStride;
+    model_update_batched(m, Pk);
+    if (which == 0)
+      for (int i = 0; i < 3; ++i) sig_w[3 * t + i] = m[12 + i];
+  }
+}
+
+__global__ void k_ladder(const double* models, uint32_t T, double opt_swap, double* ladder) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
+}
+
+}  // namespace slgpu_tier

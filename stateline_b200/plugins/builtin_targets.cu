@@ -1,0 +1,103 @@
+/*
+ * builtin_targets.cu -- the synthetic likelihoods of BASELINE.json's configs as a plugin .so
+ * (libslgpu_targets.so).  Each functor is the device form of a stateline worker's
+ *     double f(uint jobType, const std::vector<double>& x)            (src/app/workerwrapper.hpp:21)
+ * and returns a negative log-likelihood.  The first one is the reference's own demo worker
+ * (src/bin/demo-worker.cpp:37-45); the others have no code in the reference and follow SURVEY.md 8d.
+ * A user plugin looks exactly like one of these blocks.
+ */
+#include "slgpu_device.cuh"
+
+namespace {
+
+using slgpu::u32;
+
+/* config #1 -- gaussianNLL, src/bin/demo-worker.cpp:37-45: 0.5*|x|^2 for every job type */
+struct DemoGauss {
+  __device__ explicit DemoGauss(const void*) {}
+  __device__ double operator()(u32, const double* x, u32 d) const {
+    double sq = 0.0;
+#pragma unroll
+    for (u32 i = 0; i < d; ++i) sq += x[i] * x[i];
+    return 0.5 * sq;
+  }
+};
+
+/* config #2 -- 2-D double well: f(0)=8(x0^2-1)^2, f(1)=0.5*x1^2 */
+struct DoubleWell {
+  __device__ explicit DoubleWell(const void*) {}
+  __device__ double operator()(u32 job, const double* x, u32) const {
+    if (job == 0) {
+      const double t = x[0] * x[0] - 1.0;
+      return 8.0 * (t * t);
+    }
+    return 0.5 * (x[1] * x[1]);
+  }
+};
+
+/* config #3 -- factorised Gaussian: job j owns dims 2j, 2j+1; payload = mu[d], inv_s[d] */
+struct GaussFact {
+  const double* prm;
+  __device__ explicit GaussFact(const void* payload) : prm((const double*)payload) {}
+  __device__ double operator()(u32 job, const double* x, u32 d) const {
+    const double* mu = prm;
+    const double* is = prm + d;
+    const u32 a = 2 * job, b = 2 * job + 1;
+    const double ta = (x[a] - __ldg(mu + a)) * __ldg(is + a);
+    double acc = ta * ta;
+    if (b < d) {
+      const double tb = (x[b] - __ldg(mu + b)) * __ldg(is + b);
+      acc = fma(tb, tb, acc);
+    }
+    return 0.5 * acc;
+  }
+};
+
+/* config #4 -- correlated Gaussian 0.5*|U x|^2 split in J row blocks; payload = {J as double, U[d*d] row-major upper} */
+struct GaussCorr {
+  const double* prm;
+  __device__ explicit GaussCorr(const void* payload) : prm((const double*)payload) {}
+  __device__ double operator()(u32 job, const double* x, u32 d) const {
+    const u32 J = (u32)prm[0];
+    const double* U = prm + 1;
+    const u32 per = (d + J - 1) / J;
+    const u32 r0 = job * per;
+    const u32 r1 = (r0 + per < d) ? r0 + per : d;
+    double acc = 0.0;
+    for (u32 r = r0; r < r1; ++r) {
+      double dot = 0.0;
+      for (u32 c = r; c < d; ++c) dot = fma(__ldg(U + (size_t)r * d + c), x[c], dot);
+      acc = fma(dot, dot, acc);
+    }
+    return 0.5 * acc;
+  }
+};
+
+/* config #5 -- Rosenbrock/20: d-1 terms split evenly over J jobs; payload = {J as double} */
+struct Rosenbrock {
+  const double* prm;
+  __device__ explicit Rosenbrock(const void* payload) : prm((const double*)payload) {}
+  __device__ double operator()(u32 job, const double* x, u32 d) const {
+    const u32 J = (u32)prm[0];
+    const u32 nterm = d - 1;
+    const u32 per = (nterm + J - 1) / J;
+    const u32 i0 = job * per;
+    const u32 i1 = (i0 + per < nterm) ? i0 + per : nterm;
+    double acc = 0.0;
+    for (u32 i = i0; i < i1; ++i) {
+      const double a = x[i + 1] - x[i] * x[i];
+      const double b = 1.0 - x[i];
+      acc += (100.0 * (a * a) + b * b) / 20.0;
+    }
+    return acc;
+  }
+};
+
+}  // namespace
+
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_entry, DemoGauss, "demo_gauss", 0, 0, 0, 4)
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_demo_gauss, DemoGauss, "demo_gauss", 0, 0, 0, 4)
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_double_well, DoubleWell, "double_well", 2, 2, 0, 2)
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_gauss_fact, GaussFact, "gauss_fact", 0, 0, 0, 20)
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_gauss_corr, GaussCorr, "gauss_corr", 0, 0, 0)
+SLGPU_DEFINE_PLUGIN(slgpu_plugin_rosenbrock, Rosenbrock, "rosenbrock", 0, 0, 0)

@@ -1,0 +1,104 @@
+"""GPU parity: the CUDA path through the C-ABI against the CPU oracle on the same draws.
+
+Bar (north_star): fed the same recorded proposal / uniform draws, accept and swap decisions match
+exactly and fp64 chain states agree within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from stateline_b200 import configs
+from helpers import engine_for, make_replay, oracle_for, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # north_star: fp64 chain states within 1e-12 relative
+
+SMALL = {
+    "config1": dict(),                 # README demo, S=2 T=5 d=4 J=3
+    "config2": dict(S=16),             # double well, T=8 d=2
+    "config3": dict(S=12),             # 20-D factorised Gaussian, T=8
+    "config4": dict(S=3),              # 100-D correlated Gaussian, T=8 (runtime-d kernel)
+    "config5": dict(S=3),              # 50-D Rosenbrock, T=16 (runtime-d kernel)
+}
+
+
+def _compare(eng, orc, w, rounds_tag):
+    d = w["d"]
+    g_rows, o_rows = eng.last_rows(), orc.last_rows()
+    # decisions: accepted flag and swapType of every chain's last row
+    assert np.array_equal(g_rows[:, d + 3:], o_rows[:, d + 3:]), rounds_tag
+    assert rel_err(g_rows[:, :d + 3], o_rows[:, :d + 3]) <= RTOL, rounds_tag
+    gs, gb = eng.sigma_beta()
+    os_, ob = orc.sigma_beta()
+    assert rel_err(gs, os_) <= RTOL and rel_err(gb, ob) <= RTOL, rounds_tag
+    gc, oc = eng.counters(), orc.counters()
+    for k in ("length", "accepts", "swaps", "swap_attempts"):
+        assert np.array_equal(gc[k], oc[k]), (rounds_tag, k)
+    assert rel_err(gc["min_energy"], oc["min_energy"]) <= RTOL
+    for which in (0, 1):
+        gm, om = eng.models(which), orc.models(which)
+        assert np.array_equal(gm[3], om[3])  # counts
+        assert rel_err(gm[0], om[0]) <= 1e-11 and rel_err(gm[1], om[1]) <= 1e-11
+        assert np.allclose(gm[2], om[2], rtol=1e-9, atol=1e-12)  # weights: 3x3 solve, cond*eps
+    for chain in (0, w["T"] - 1, w["S"] * w["T"] - 1):
+        gL, gN, gcnt = eng.shaper(chain)
+        oL, oN, ocnt = orc.shaper(chain)
+        assert gcnt == ocnt
+        assert rel_err(gL, oL) <= RTOL and rel_err(gN, oN) <= RTOL
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_replay_exact(name):
+    w = configs.workload(name, **SMALL[name])
+    n_rounds = 45 if w["d"] <= 20 else 25
+    z, u_mh, u_swap, x_init = make_replay(w["S"], w["T"], w["d"], n_rounds, seed=sum(map(ord, name)))
+    orc = oracle_for(w, rng_mode=O.RNG_REPLAY)
+    orc.set_replay(z, u_mh, u_swap, x_init)
+    orc.init_chains()
+    with engine_for(w, rng="replay") as eng:
+        eng.set_replay(z, u_mh, u_swap, x_init)
+        eng.init_chains()
+        _compare(eng, orc, w, "init")
+        done = 0
+        for chunk in (1, 7, 2, n_rounds - 10):  # uneven chunks: launches split at adapt points
+            orc.run_rounds(chunk)
+            eng.step_rounds(chunk)
+            done += chunk
+            _compare(eng, orc, w, "after %d rounds" % done)
+        # cold-chain rows, emission order: initial row then one per round, per stack
+        rows = eng.drain()
+        assert rows.shape == ((done + 1) * w["S"], w["d"] + 5)
+        rows = rows.reshape(done + 1, w["S"], w["d"] + 5)
+        for s in range(w["S"]):
+            o = orc.cold_rows(s)
+            assert o.shape[0] == done + 1
+            assert np.array_equal(rows[:, s, w["d"] + 3:], o[:, w["d"] + 3:])
+            assert rel_err(rows[:, s, :w["d"] + 3], o[:, :w["d"] + 3]) <= RTOL
+        if w["S"] >= 2:
+            assert np.allclose(eng.rhat(), orc.rhat(), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("name", ["config1", "config3"])
+def test_philox_matches_oracle(name):
+    """Native Philox streams: the kernel draws the same normals / uniforms as the oracle's scheme
+    (libm ulp differences only), so short runs still agree to 1e-12."""
+    w = configs.workload(name, **SMALL[name])
+    orc = oracle_for(w, seed=77, stack_offset=5)
+    orc.init_chains()
+    orc.run_rounds(39)
+    with engine_for(w, seed=77, stack_offset=5) as eng:
+        eng.init_chains()
+        eng.step_rounds(39)
+        _compare(eng, orc, w, "philox 39 rounds")
+
+
+@pytest.mark.parametrize("name", list(SMALL))
+def test_likelihood_contract(name):
+    """f(job, x) of the device functor == the oracle's target on random points, and energy = sum over jobs."""
+    w = configs.workload(name, **SMALL[name])
+    rng = np.random.default_rng(3)
+    x = rng.uniform(np.array(w["mn"]), np.array(w["mx"]), (64, w["d"]))
+    with engine_for(w, sink="none") as eng:
+        got = eng.eval_likelihood(x)
+    want = np.array([[O.target_eval(w["oracle_target"], w["oracle_params"], w["d"], w["J"], j, xi) for j in range(w["J"])] for xi in x])
+    assert rel_err(got, want) <= 1e-14

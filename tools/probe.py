@@ -1,0 +1,32 @@
+"""Quick device-time probe of the step loop on one workload (development aid, not the bench)."""
+import argparse
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stateline_b200 import Engine, configs
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="config3")
+ap.add_argument("--stacks", type=int, default=None)
+ap.add_argument("--warm", type=int, default=200)
+ap.add_argument("--rounds", type=int, default=500)
+ap.add_argument("--sink", default="device")
+a = ap.parse_args()
+w = configs.workload(a.workload, S=a.stacks)
+with Engine(configs.engine_config(w, sink=a.sink, overwrite=True), plugin=w["plugin"], payload=w["payload"]) as e:
+    e.init_chains()
+    e.step_rounds(a.warm)
+    e.sync()
+    for rep in range(3):
+        e.timer_start()
+        e.step_rounds(a.rounds)
+        ms = e.timer_stop()
+        e.sync()
+        cs = w["S"] * w["T"] * a.rounds
+        print(json.dumps({"workload": a.workload, "S": w["S"], "T": w["T"], "d": w["d"], "rounds": a.rounds, "ms": ms,
+                          "us_per_round": 1e3 * ms / a.rounds, "chain_steps_per_s": cs / (ms * 1e-3)}))
+    s = e.summary()
+    print(json.dumps({k: s[k] for k in ("accept_rate", "swap_rate", "sigma", "beta")}))
+    print("rhat mean", sum(s["rhat"]) / max(1, len(s["rhat"])))
