@@ -136,6 +136,10 @@ slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_
 /* one State row as CSVChainArrayWriter prints it (db.cpp:18-25), no newline; returns the length */
 size_t slgpu_format_row(const double* row, uint32_t d, char* out, size_t cap);
 
+/* measurement aid: sustained FP64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA) from a
+ * register-resident DFMA loop; the denominator of the fp64 roofline fraction bench.py reports */
+slgpu_status slgpu_measure_fp64_peak(int device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -398,6 +398,21 @@ slgpu_status sync_all(slgpu_engine* e) {
   return SLGPU_OK;
 }
 
+// 16 independent DFMA chains per thread: the FP64 FMA pipe roof that roofline fractions are quoted against
+__global__ void k_dfma_peak(double* sink, int iters, double m) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, 1e-12);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456) *sink = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -998,5 +1013,36 @@ slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_
 }
 
 size_t slgpu_format_row(const double* row, uint32_t d, char* out, size_t cap) { return format_row(row, d, out, cap); }
+
+slgpu_status slgpu_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(SLGPU_E_ARG, "tflops must not be NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(SLGPU_E_CUDA, "no such CUDA device");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  double* sinkbuf = nullptr;
+  CU_TRY(cudaMalloc((void**)&sinkbuf, sizeof(double)));
+  cudaEvent_t a, b;
+  CU_TRY(cudaEventCreate(&a));
+  CU_TRY(cudaEventCreate(&b));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU_TRY(cudaEventRecord(a));
+    k_dfma_peak<<<blocks, threads>>>(sinkbuf, iters, 1.0000001);
+    CU_TRY(cudaEventRecord(b));
+    CU_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    if (rep >= 2) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sinkbuf);
+  *tflops = best;
+  return SLGPU_OK;
+}
 
 }  // extern "C"

@@ -28,7 +28,7 @@ SYMBOLS = [
     "slgpu_timer_stop", "slgpu_launch_count", "slgpu_n_dims", "slgpu_n_chains", "slgpu_get_last_rows",
     "slgpu_get_sigma_beta", "slgpu_get_shaper", "slgpu_get_models", "slgpu_get_ladder",
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
-    "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row",
+    "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
 ]
 
 BUILTIN_ENTRIES = {
@@ -96,6 +96,7 @@ def lib():
     L.slgpu_eval_likelihood.argtypes = [C.c_void_p, _dp, C.c_uint32, _dp]
     L.slgpu_format_row.argtypes = [_dp, C.c_uint32, C.c_char_p, C.c_size_t]
     L.slgpu_format_row.restype = C.c_size_t
+    L.slgpu_measure_fp64_peak.argtypes = [C.c_int, _dp]
     _lib = L
     return L
 
@@ -313,6 +314,13 @@ class Engine:
         out = np.empty((x.shape[0], self.J))
         _check(lib().slgpu_eval_likelihood(self.h, _p(x), x.shape[0], _p(out)))
         return out
+
+
+def measure_fp64_peak(device=0):
+    """Sustained FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA loop)."""
+    v = C.c_double()
+    _check(lib().slgpu_measure_fp64_peak(int(device), C.byref(v)))
+    return v.value
 
 
 def rhat_finish(sum_dm2, sum_s, n_stacks_total, n_samples):

@@ -34,3 +34,14 @@ def rel_err(a, b):
         e = np.abs(a - b) / den
     e[(a == b)] = 0.0
     return float(np.max(e)) if e.size else 0.0
+
+
+def scaled_err(a, b, scale):
+    """max |a-b| / max(|b|, scale): relative error that does not blow up on entries that are small
+    only through cancellation (a coordinate near 0 inside a [-10,10] box, an energy near its minimum)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), scale)
+    with np.errstate(invalid="ignore"):
+        e = np.abs(a - b) / den
+    e[(a == b)] = 0.0
+    return float(np.max(e)) if e.size else 0.0
