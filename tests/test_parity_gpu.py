@@ -51,7 +51,8 @@ def _compare(eng, orc, w, rounds_tag):
         gL, gN, gcnt = eng.shaper(chain)
         oL, oN, ocnt = orc.shaper(chain)
         assert gcnt == ocnt
-        assert rel_err(gL, oL) <= RTOL and rel_err(gN, oN) <= RTOL
+        # factors: error relative to the largest entry (off-diagonals pass through sums with cancellation)
+        assert scaled_err(gL, oL, np.abs(oL).max()) <= RTOL and scaled_err(gN, oN, np.abs(oN).max()) <= RTOL
 
 
 @pytest.mark.parametrize("name", list(SMALL))
