@@ -31,7 +31,12 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
+#include <type_traits>
+
+#include "slgpu_math.h"
 #include "slgpu_plugin.h"
 
 #ifndef SLGPU_THREADS
@@ -62,10 +67,12 @@ __device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u3
 __device__ __forceinline__ void philox_draw(u64 seed, u32 chain, u64 round, u32 purpose, u32 block, double& ua, double& ub) {
   u32 o[4];
   philox4x32_10((u32)round, chain, (purpose & 0xffu) | ((u32)(round >> 32) << 8), block, (u32)seed, (u32)(seed >> 32), o);
+  /* (k52 + 0.5) * 2^-52 with k52 the top 52 bits, built exactly without an integer->double conversion:
+   * [1,2) double from the mantissa bits, minus 1 (exact), plus 2^-53 (exact: 2 k52 + 1 < 2^53) */
   const u64 a = (((u64)o[1] << 32) | o[0]) >> 12;
   const u64 b = (((u64)o[3] << 32) | o[2]) >> 12;
-  ua = ((double)a + 0.5) * 2.220446049250313080847263336181640625e-16;
-  ub = ((double)b + 0.5) * 2.220446049250313080847263336181640625e-16;
+  ua = (__longlong_as_double((long long)(a | 0x3ff0000000000000ull)) - 1.0) + 1.1102230246251565404236316680908203125e-16;
+  ub = (__longlong_as_double((long long)(b | 0x3ff0000000000000ull)) - 1.0) + 1.1102230246251565404236316680908203125e-16;
 }
 
 /* std::max / std::min comparison order (NaN handling as on the host) */
@@ -172,6 +179,26 @@ __device__ __forceinline__ double shaper_update(double* __restrict__ Lc, size_t 
   return prop_norm / smax(frob, eps);
 }
 
+/* Optional compile-time job count: a functor may declare
+ *     template <int D> static constexpr int static_job_types();
+ * so that the sum over job types unrolls (static indexing keeps x in registers).  0 = run-time count. */
+template <class L, int D, class = void>
+struct StaticJobs { static constexpr int value = 0; };
+template <class L, int D>
+struct StaticJobs<L, D, std::void_t<decltype(L::template static_job_types<D>())>> {
+  static constexpr int value = L::template static_job_types<D>();
+};
+
+/* base of chain c's packed L inside its 128-chain tile; consecutive entries are SLGPU_L_TILE doubles apart */
+__device__ __forceinline__ double* l_base(double* L, u32 c, u32 nL) {
+  return L + (size_t)(c / SLGPU_L_TILE) * nL * SLGPU_L_TILE + (c % SLGPU_L_TILE);
+}
+
+/* regression statistics: P[(k*T + t)*S + s], k < 9 -- coalesced over the stacks of a tier for the reduce */
+__device__ __forceinline__ size_t pidx(const slgpu_step_params& p, int k, int t, u32 s) {
+  return ((size_t)k * p.n_temps + (size_t)t) * p.n_stacks + s;
+}
+
 struct ThreadMap {
   int T, lane, sl, t, base, spw;
   u32 s, c;
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
     p.x[(size_t)i * C + c] = x[i];
   for (int r = 0; r < d; ++r)
     for (int k = 0; k <= r; ++k)
-      p.L[(size_t)(r * (r + 1) / 2 + k) * C + c] = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
+      l_base(p.L, c, (u32)(d * (d + 1) / 2))[(size_t)(r * (r + 1) / 2 + k) * SLGPU_L_TILE] = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
   const double b = p.ladder[m.t];
   p.energy[c] = e;
   p.row_sigma[c] = 1.0;
@@ -254,8 +281,8 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
   p.lg_swap_attempts[c] = 1;
   p.lg_min_energy[c] = __longlong_as_double(0x7ff0000000000000LL);
   for (int k = 0; k < 9; ++k) {
-    p.p_sig[(size_t)k * C + c] = 0.0;
-    p.p_beta[(size_t)k * C + c] = 0.0;
+    p.p_sig[pidx(p, k, m.t, m.s)] = 0.0;
+    p.p_beta[pidx(p, k, m.t, m.s)] = 0.0;
   }
   if (m.t == 0) {
     for (int i = 0; i < d; ++i) {
@@ -305,14 +332,14 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
   double* P = s_P + threadIdx.x; /* P[k*SLGPU_THREADS], k<9 sigma statistics, 9..17 beta statistics */
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
-    P[k * SLGPU_THREADS] = p.p_sig[(size_t)k * C + c];
-    P[(9 + k) * SLGPU_THREADS] = p.p_beta[(size_t)k * C + c];
+    P[k * SLGPU_THREADS] = active ? p.p_sig[pidx(p, k, m.t, m.s)] : 0.0;
+    P[(9 + k) * SLGPU_THREADS] = active ? p.p_beta[pidx(p, k, m.t, m.s)] : 0.0;
   }
   __syncthreads();
 
   const Lik lik(p.payload);
-  double* __restrict__ Lc = p.L + c;
-  const size_t ls = C;
+  double* __restrict__ Lc = l_base(p.L, c, (u32)(d * (d + 1) / 2));
+  const size_t ls = SLGPU_L_TILE;
 
   double x[DM];
 #pragma unroll
@@ -341,10 +368,9 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
         for (int k = 0; k < (d + 1) / 2; ++k) {
           double ua, ub;
           philox_draw(p.seed, gchain, r, 0, (u32)k, ua, ub);
-          const double R = sqrt(-2.0 * log(ua));
-          const double th = 6.283185307179586476925286766559 * ub;
+          const double R = sqrt(-2.0 * slm_log(ua));
           double sn, cs;
-          sincos(th, &sn, &cs);
+          slm_sincos2pi(ub, &sn, &cs);
           z[2 * k] = R * cs;
           if (2 * k + 1 < d) z[2 * k + 1] = R * sn;
         }
@@ -370,7 +396,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
         if (p.rng_mode == SLGPU_RNG_REPLAY) u = p.rp_umh[(size_t)r * C + c];
         else { double ub; philox_draw(p.seed, gchain, r, 1, 0, u, ub); }
         const double deltaEnergy = e_new - energy;
-        const double pr = exp(-1.0 * beta * deltaEnergy);
+        const double pr = slm_exp(-1.0 * beta * deltaEnergy);
         acc = u < pr;
       }
       if (acc) {
@@ -387,9 +413,9 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
       accepted = acc ? 1 : 0;
       swap_type = 0;
       /* ---- sigma adaptation, sampler.cpp:160-162 (statistics summed, model frozen) ---- */
-      const double logtemper = -log(row_beta);
-      stats_accumulate<SLGPU_THREADS>(P, -8.0, 4.0, log(row_sigma), logtemper, acc);
-      sigma = exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
+      const double logtemper = -slm_log(row_beta);
+      stats_accumulate<SLGPU_THREADS>(P, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
+      sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
       /* ---- proposal shape, sampler.cpp:165-166 ---- */
       if (acc) nscale = shaper_update<D>(Lc, ls, d, xp, sh_count, p.prop_norm);
     }
@@ -414,14 +440,14 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
         const double u = shfl_d(u_sw, m.base + tt);
         const double deltaEnergy = El - Eh;
         const double deltaBeta = bl - bh;
-        const bool sw = u < exp(deltaEnergy * deltaBeta);
+        const bool sw = u < slm_exp(deltaEnergy * deltaBeta);
         if (m.t == tt + 1) my_src = sw ? tt : cur;
         if (m.t == tt) { my_swapped = sw; mid_src = sw ? cur : tt; }
         if (!sw) cur = tt;
       }
       if (m.t == 0) my_src = cur;
       /* beta statistics of pair (t, t+1): betaUpdate adaptive.cpp:108-116 */
-      const double lb = log(beta);
+      const double lb = slm_log(beta);
       const double lbh = shfl_d(lb, m.lane + 1 < 32 ? m.lane + 1 : m.lane);
       mid_e = shfl_d(energy, m.base + mid_src);
       mid_acc = __shfl_sync(0xffffffffu, accepted, m.base + mid_src);
@@ -492,11 +518,17 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
     p.lg_min_energy[c] = lg_min_e;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      p.p_sig[(size_t)k * C + c] = P[k * SLGPU_THREADS];
-      p.p_beta[(size_t)k * C + c] = P[(9 + k) * SLGPU_THREADS];
+      p.p_sig[pidx(p, k, m.t, m.s)] = P[k * SLGPU_THREADS];
+      p.p_beta[pidx(p, k, m.t, m.s)] = P[(9 + k) * SLGPU_THREADS];
     }
   }
 }
+
+}  // namespace slgpu
+
+#include "slgpu_step_fast.cuh"
+
+namespace slgpu {
 
 /* contract check: nll[point*J + job] = f(job, x[point]) */
 template <class Lik>
@@ -509,10 +541,20 @@ __global__ void lik_eval_kernel(const slgpu_step_params p, const double* __restr
   for (u32 j = 0; j < p.n_job_types; ++j) nll[(size_t)i * p.n_job_types + j] = lik(j, x, p.n_dims);
 }
 
-inline unsigned grid_for(const slgpu_step_params* p) {
+inline unsigned grid_for(const slgpu_step_params* p, unsigned threads = SLGPU_THREADS) {
   const unsigned spw = 32u / p->n_temps;
-  const unsigned per_block = spw * (SLGPU_THREADS / 32);
+  const unsigned per_block = spw * (threads / 32);
   return (p->n_stacks + per_block - 1) / per_block;
+}
+
+/* development switch: SLGPU_STEP_VARIANT=generic forces the runtime-d kernel */
+inline int step_variant() {
+  const char* v = getenv("SLGPU_STEP_VARIANT");
+  if (!v) return 0;
+  if (!strcmp(v, "smem")) return 1;
+  if (!strcmp(v, "global")) return 2;
+  if (!strcmp(v, "generic")) return 3;
+  return 0;
 }
 
 /* host launchers instantiated per (functor, compile-time dimension); D = 0 is the runtime-d kernel */
@@ -523,6 +565,18 @@ int launch_init_t(const slgpu_step_params* p, void* stream) {
 }
 template <class Lik, int D>
 int launch_step_t(const slgpu_step_params* p, void* stream) {
+  constexpr int JS = StaticJobs<Lik, D>::value;
+  if (JS > 0 && p->n_job_types != (uint32_t)JS) {
+    pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
+    return (int)cudaGetLastError();
+  }
+  if constexpr (D > 0 && D <= 32) {
+    if (step_variant() != 3) {
+      constexpr int NT = SLGPU_FAST_THREADS;
+      pt_step_fast_kernel<Lik, D, NT><<<grid_for(p, NT), NT, 0, (cudaStream_t)stream>>>(*p);
+      return (int)cudaGetLastError();
+    }
+  }
   pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
   return (int)cudaGetLastError();
 }

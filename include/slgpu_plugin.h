@@ -25,6 +25,7 @@ extern "C" {
 #define SLGPU_PLUGIN_ABI 1u
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
+#define SLGPU_L_TILE 128u   /* chains per tile of the packed-L store (see slgpu_step_params.L) */
 #define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
 
 enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
@@ -32,8 +33,10 @@ enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
 /* Everything a launch needs.  All pointers are device pointers owned by the engine.
  * Chain id = stack * n_temps + temperature, temperature 0 coldest (src/infer/chainarray.hpp:28-37).
  * C = n_stacks * n_temps.  Per-chain arrays are indexed [chain]; vectors and matrices are stored
- * structure-of-arrays, element-major: x[i * C + chain], L[(r*(r+1)/2 + k) * C + chain] (packed lower
- * triangle, row-major), p_sig[k * C + chain], ep_m[i * n_stacks + stack]. */
+ * structure-of-arrays, element-major: x[i * C + chain]; the packed lower triangle of L (row-major, nL =
+ * d(d+1)/2 entries) is tiled by 128 chains, L[((chain / 128) * nL + r*(r+1)/2 + k) * 128 + chain % 128], so a
+ * warp reads one 256-byte line per entry, a thread block's factors are one contiguous region and
+ * the entry offsets inside a tile are compile-time constants; p_sig[(k * T + temp) * S + stack], ep_m[i * n_stacks + stack]. */
 typedef struct slgpu_step_params {
   uint32_t n_stacks, n_temps, n_dims, n_job_types;
   uint32_t swap_interval;  /* swap sweep in the round that makes the chain length a multiple of it */
@@ -52,7 +55,7 @@ typedef struct slgpu_step_params {
   const double* initial;   /* [d] or NULL (useInitial) */
   /* chain state */
   double* x;               /* [d][C]  sample of the last row */
-  double* L;               /* [d(d+1)/2][C]  ProposalShaper L_ (adaptive.cpp:158) */
+  double* L;               /* [ceil(C/128)][d(d+1)/2][128]  ProposalShaper L_ (adaptive.cpp:158) */
   double* energy;          /* [C] */
   double* row_sigma;       /* [C] sigma stored in the last row (stale after a reject, chainarray.cpp:102-106) */
   double* row_beta;        /* [C] */
@@ -71,8 +74,8 @@ typedef struct slgpu_step_params {
   const double* sig_w;     /* [T][3] weights of the sigma regression */
   const double* ladder;    /* [T] beta ladder from the last adapt point */
   /* regression sufficient statistics gathered since the last adapt point */
-  double* p_sig;           /* [9][C] */
-  double* p_beta;          /* [9][C] */
+  double* p_sig;           /* [9][T][S] */
+  double* p_beta;          /* [9][T][S] */
   /* EPSRDiagnostic Welford state of the cold chains (src/infer/diagnostics.cpp:27-47) */
   double* ep_m;            /* [d][S] */
   double* ep_s;            /* [d][S] */

@@ -1,0 +1,398 @@
+/*
+ * slgpu_step_fast.cuh -- pt_step for a compile-time dimension D <= 32 (included by slgpu_device.cuh).
+ *
+ * Same rounds, same arithmetic in the same order as pt_step_kernel and the oracle; what differs is
+ * how the work is laid on the SM:
+ *   - one thread per chain, x / x' / the row sums live in registers (static indexing only);
+ *   - loops over the column index k stay ROLLED (the instruction stream of a fully unrolled d=20
+ *     step is ~250 KB and thrashes the instruction caches); the loops over the row index are unrolled
+ *     and guarded by warp-uniform branches on k, so the triangular structure costs no wasted lanes;
+ *   - the proposal GEMV runs column by column while the normals are generated, so z is never stored;
+ *   - the packed L factors stay in global memory, chain-minor ([idx][chain]): every access of a warp is
+ *     one coalesced 256-byte line, and a block's factors (128 chains x 1.7 KB) stay L2-resident over
+ *     the rounds of a launch, so HBM sees them about once per launch;
+ *   - ProposalShaper::update runs only for accepted proposals (~23%).  Done in place it would drag all
+ *     32 lanes of a warp through ~7000 instructions for ~7 useful lanes, so the accepted chains of a block
+ *     are COMPACTED: phase A stages (jump vector, chain id, count) of each accepted chain in shared
+ *     memory, phase B lets threads 0..n_acc-1 each update one staged chain with full lanes, and the new
+ *     N scale is handed back to the owning thread.  Two block barriers per round.
+ */
+#ifndef SLGPU_STEP_FAST_CUH
+#define SLGPU_STEP_FAST_CUH
+
+namespace slgpu {
+
+/* n / c given rc = RN(1/c): q0 = RN(n rc), r = n - q0 c (exact, fma), q = RN(q0 + r rc).  By Markstein's
+ * theorem this is the correctly rounded quotient -- the same bits as the IEEE division the reference
+ * and the oracle perform -- at 3 fp64 instructions instead of ~12+ (tests/test_math.py checks 10^8 cases). */
+__device__ __forceinline__ double div_by(double n, double c, double rc) {
+  const double q0 = n * rc;
+  const double r = fma(-q0, c, n);
+  return fma(r, rc, q0);
+}
+
+#ifndef SLGPU_FAST_MINBLOCKS
+#define SLGPU_FAST_MINBLOCKS 2
+#endif
+#ifndef SLGPU_FAST_THREADS
+#define SLGPU_FAST_THREADS 128
+#endif
+#ifndef SLGPU_COLBLOCK
+#define SLGPU_COLBLOCK 4
+#endif
+
+constexpr int kLs = (int)SLGPU_L_TILE; /* doubles between consecutive packed entries of a chain's L */
+constexpr int kColBlock = SLGPU_COLBLOCK; /* columns per block of the blocked triangular sweeps */
+
+/* Columns K0..K0+KB-1 of the proposal GEMV: a_j = fma(N_jk, z_k, a_j) for j >= k.  Rows j >= K0 are
+ * loaded unconditionally (for K0 <= j < k the address is still inside the packed triangle, the value is
+ * ignored), so a column's loads issue back to back; only the first KB rows need the j >= k guard. */
+template <int D, int K0, int KB>
+__device__ __forceinline__ void gemv_block(const double* Lc, const double* zs, int zstride, double nscale, bool fresh,
+                                           const double* s_n0, double* a) {
+  constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
+#pragma unroll 1
+  for (int k = K0; k < K1; ++k) {
+    const double zk = zs[k * zstride];
+    const double* Lk = Lc + k * kLs;
+    double col[D];
+#pragma unroll
+    for (int j = K0; j < D; ++j) col[j] = Lk[(j * (j + 1) / 2) * kLs];
+    const double n0k = s_n0[k];
+#pragma unroll
+    for (int j = K0; j < D; ++j) {
+      if (j >= K1 || j >= k) { /* static for j >= K1, warp-uniform otherwise */
+        double njk = col[j] * nscale;
+        if (j < K1 && j == k) njk = fresh ? n0k : njk + 1e-4;
+        a[j] = fma(njk, zk, a[j]);
+      }
+    }
+  }
+  if constexpr (K1 < D) gemv_block<D, K1, KB>(Lc, zs, zstride, nscale, fresh, s_n0, a);
+}
+
+/* Columns K0..K0+KB-1 of ProposalShaper::update's rank-1 sweep (src/infer/adaptive.cpp:184-197). */
+template <int D, int K0, int KB>
+__device__ __forceinline__ void shaper_block(double* Lc, double scale, double* xs, double* fr, double& xk, double* diag,
+                                             int dstride) {
+  constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
+  const double eps = 1e-18;
+#pragma unroll 1
+  for (int k = K0; k < K1; ++k) {
+    double* Lk = Lc + k * kLs; /* column k: L(j,k) = Lk[(j(j+1)/2)*ls] */
+    double col[D];
+#pragma unroll
+    for (int j = K0; j < D; ++j) col[j] = Lk[(j * (j + 1) / 2) * kLs];
+    double Lkk = col[K0];
+#pragma unroll
+    for (int j = K0 + 1; j < K1; ++j) Lkk = (j == k) ? col[j] : Lkk;
+    Lkk = Lkk * scale;
+    const double V = smax(eps, Lkk);
+    const double rV = 1.0 / V;
+    const double r = sqrt(V * V + xk * xk);
+    const double c = div_by(r, V, rV);
+    const double s = div_by(xk, V, rV);
+    const double rc = 1.0 / c;
+    Lk[(k * (k + 1) / 2) * kLs] = r;
+    diag[k * dstride] = r;
+    double xnext = 0.0;
+#pragma unroll
+    for (int j = K0 + 1; j < D; ++j) {
+      if (j >= K1 || j > k) { /* static for j >= K1, warp-uniform otherwise */
+        double Ljk = col[j] * scale;
+        Ljk = div_by(Ljk + s * xs[j], c, rc);
+        Lk[(j * (j + 1) / 2) * kLs] = Ljk;
+        xs[j] = c * xs[j] - s * Ljk;
+        fr[j] = fma(Ljk, Ljk, fr[j]);
+        if (j <= K1) xnext = (j == k + 1) ? xs[j] : xnext;
+      }
+    }
+    xk = xnext;
+  }
+  if constexpr (K1 < D) shaper_block<D, K1, KB>(Lc, scale, xs, fr, xk, diag, dstride);
+}
+
+/* ProposalShaper::update (src/infer/adaptive.cpp:173-209), blocked column sweep; Lc[(r(r+1)/2+k)*ls].
+ * diag[k*dstride] is scratch (shared memory) for the new diagonal, so no register array is indexed by k. */
+template <int D>
+__device__ __forceinline__ double shaper_update_rolled(double* Lc, double* xs, double count, double prop_norm,
+                                                        double* diag, int dstride) {
+  const double eps = 1e-18;
+  const double sq = sqrt(count);
+  const double rsq = 1.0 / sq;
+  const double scale = sqrt((count - 1.0) / count);
+  double fr[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    xs[i] = div_by(xs[i], sq, rsq);
+    fr[i] = 0.0;
+  }
+  double xk = xs[0];
+  shaper_block<D, 0, kColBlock>(Lc, scale, xs, fr, xk, diag, dstride);
+  /* the diagonal is the last entry of each row sum */
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const double dj = diag[j * dstride];
+    fr[j] = fma(dj, dj, fr[j]);
+  }
+  /* |L|_F: slot l = row sum l (D <= 32), halving tree over 32 slots; slots >= D are +0 and are skipped */
+  int nlive = D;
+#pragma unroll
+  for (int mm = 16; mm > 0; mm >>= 1) {
+#pragma unroll
+    for (int l = 0; l < mm; ++l)
+      if (l + mm < D && l + mm < nlive) fr[l] += fr[l + mm];
+    if (nlive > mm) nlive = mm;
+  }
+  const double frob = sqrt(fr[0]);
+  return prop_norm / smax(frob, eps);
+}
+
+template <class Lik, int D, int NT>
+__global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(const slgpu_step_params p) {
+  const ThreadMap m(p);
+  const int T = m.T;
+  const size_t C = (size_t)p.n_stacks * p.n_temps;
+  const bool active = m.active;
+  const u32 c = active ? m.c : 0u;
+  const u32 gchain = p.stack_offset * p.n_temps + c;
+  const bool replay = (p.rng_mode == SLGPU_RNG_REPLAY);
+  const int tid = threadIdx.x;
+
+  __shared__ double s_mn[D], s_mx[D], s_n0[D];
+  __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
+  __shared__ double s_jump[D * NT]; /* staged accepted jumps, [i][slot] */
+  __shared__ double s_z[D * NT];    /* this round's normals, [k][thread] */
+  __shared__ double s_cnt[NT];      /* shaper count (already incremented) of the staged chain */
+  __shared__ double s_nsc[NT];      /* result: new N scale, indexed by owning thread */
+  __shared__ u32 s_chain[NT];       /* chain id of the staged chain */
+  __shared__ u32 s_owner[NT];       /* owning thread of the staged chain */
+  __shared__ int s_nacc[2];
+  for (int i = tid; i < D; i += NT) {
+    s_mn[i] = p.mn[i];
+    s_mx[i] = p.mx[i];
+    s_n0[i] = p.n0_diag[i];
+  }
+  for (int i = tid; i < T; i += NT) {
+    s_w[3 * i + 0] = p.sig_w[3 * i + 0];
+    s_w[3 * i + 1] = p.sig_w[3 * i + 1];
+    s_w[3 * i + 2] = p.sig_w[3 * i + 2];
+    s_lad[i] = p.ladder[i];
+  }
+  if (tid < 2) s_nacc[tid] = 0;
+  __syncthreads();
+
+  const Lik lik(p.payload);
+  const double* Lc = l_base(p.L, c, D * (D + 1) / 2); /* rewritten by other threads in phase B: no __restrict__ */
+  double x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = p.x[(size_t)i * C + c];
+  double Ps[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Ps[k] = active ? p.p_sig[pidx(p, k, m.t, m.s)] : 0.0;
+  double energy = p.energy[c], row_sigma = p.row_sigma[c], row_beta = p.row_beta[c];
+  double sigma = p.sigma[c], beta = p.beta[c], nscale = p.nscale[c], sh_count = p.sh_count[c];
+  int accepted = p.accepted[c], swap_type = p.swap_type[c];
+  u32 lg_accepts = p.lg_accepts[c], lg_swaps = p.lg_swaps[c], lg_att = p.lg_swap_attempts[c];
+  double lg_min_e = p.lg_min_energy[c];
+  const double w3[3] = {s_w[3 * m.t], s_w[3 * m.t + 1], s_w[3 * m.t + 2]};
+  const int W = (int)p.swap_interval;
+
+  for (u32 it = 0; it < p.n_rounds; ++it) {
+    const u64 r = p.round_begin + it;
+    const int par = (int)(it & 1u);
+    bool acc = false;
+    /* ================= phase A: propose, evaluate, accept, sigma ================= */
+    if (active) {
+      const bool fresh = (sh_count == p.sh_count0);
+      const double* zr = replay ? p.rp_z + ((size_t)r * C + c) * D : nullptr;
+      double a[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) a[i] = 0.0;
+      /* the round's normals go to this thread's column of s_z (rolled loop: one copy of the generator) */
+#pragma unroll 1
+      for (int kp = 0; kp < (D + 1) / 2; ++kp) {
+        double z0, z1 = 0.0;
+        if (replay) {
+          z0 = zr[2 * kp];
+          if (2 * kp + 1 < D) z1 = zr[2 * kp + 1];
+        } else {
+          double ua, ub, sn, cs;
+          philox_draw(p.seed, gchain, r, 0, (u32)kp, ua, ub);
+          const double R = sqrt(-2.0 * slm_log(ua));
+          slm_sincos2pi(ub, &sn, &cs);
+          z0 = R * cs;
+          z1 = R * sn;
+        }
+        s_z[(2 * kp) * NT + tid] = z0;
+        if (2 * kp + 1 < D) s_z[(2 * kp + 1) * NT + tid] = z1;
+      }
+      /* GaussianProposal::propose (sampler.cpp:79-88): a_i = sum_{k<=i} fma(N_ik, z_k, .), k ascending */
+      gemv_block<D, 0, kColBlock>(Lc, s_z + tid, NT, nscale, fresh, s_n0, a);
+#pragma unroll
+      for (int i = 0; i < D; ++i) a[i] = bounce1(x[i] + a[i] * sigma, s_mn[i], s_mx[i]);
+      /* energy = sum over job types in order (sampler.cpp:148-150) */
+      double e_new = 0.0;
+      if constexpr (StaticJobs<Lik, D>::value > 0) {
+#pragma unroll
+        for (u32 j = 0; j < (u32)StaticJobs<Lik, D>::value; ++j) e_new += lik(j, a, (u32)D);
+      } else {
+        for (u32 j = 0; j < p.n_job_types; ++j) e_new += lik(j, a, (u32)D);
+      }
+      /* acceptProposal (chainarray.cpp:30-45) + append (:94-121) */
+      if (!isinf(e_new)) {
+        double u;
+        if (replay) u = p.rp_umh[(size_t)r * C + c];
+        else { double ub; philox_draw(p.seed, gchain, r, 1, 0, u, ub); }
+        const double deltaEnergy = e_new - energy;
+        acc = u < slm_exp(-1.0 * beta * deltaEnergy);
+      }
+      if (acc) {
+        const int slot = atomicAdd(&s_nacc[par], 1);
+        sh_count += 1.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double nx = a[i];
+          s_jump[i * NT + slot] = nx - x[i]; /* the accepted jump (sampler.cpp:166) */
+          x[i] = nx;
+        }
+        s_cnt[slot] = sh_count;
+        s_chain[slot] = c;
+        s_owner[slot] = (u32)tid;
+        energy = e_new;
+        row_sigma = sigma;
+        row_beta = beta;
+      }
+      accepted = acc ? 1 : 0;
+      swap_type = 0;
+      /* sigma adaptation (sampler.cpp:160-162): statistics summed, model frozen for the launch */
+      const double logtemper = -slm_log(row_beta);
+      stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
+      sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
+    }
+    /* park x in this thread's (now dead) column of s_z while phase B needs the registers */
+#pragma unroll
+    for (int i = 0; i < D; ++i) s_z[i * NT + tid] = x[i];
+    __syncthreads();
+    /* ================= phase B: compacted ProposalShaper updates ================= */
+    {
+      const int nacc = s_nacc[par];
+      /* slot -> thread map that spreads the staged chains over all warps (lane-major): with few warps
+       * resident per SM, parallel half-empty warps beat one full warp */
+      const int slot = (tid & 31) * (NT / 32) + (tid >> 5);
+      if (slot < nacc) {
+        double xs[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xs[i] = s_jump[i * NT + slot];
+        s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), xs, s_cnt[slot], p.prop_norm, s_jump + slot, NT);
+      }
+      if (tid == 0) s_nacc[par ^ 1] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = s_z[i * NT + tid];
+    if (acc) nscale = s_nsc[tid];
+
+    /* ================= swap sweep, hottest pair first ================= */
+    double mid_e = energy;
+    int mid_acc = accepted;
+    const bool swapRound = (T > 1) && ((r + 2) % (u64)W == 0);
+    if (swapRound) {
+      double u_sw = 0.0;
+      if (active && m.t < T - 1) {
+        if (replay) u_sw = p.rp_uswap[(size_t)r * C + c];
+        else { double ub; philox_draw(p.seed, gchain, r, 2, 0, u_sw, ub); }
+      }
+      int cur = T - 1, my_src = m.t, mid_src = m.t;
+      bool my_swapped = false;
+      for (int tt = T - 2; tt >= 0; --tt) {
+        const double El = shfl_d(energy, m.base + tt);
+        const double Eh = shfl_d(energy, m.base + cur);
+        const double bl = shfl_d(beta, m.base + tt);
+        const double bh = shfl_d(beta, m.base + tt + 1);
+        const double u = shfl_d(u_sw, m.base + tt);
+        const double deltaEnergy = El - Eh;
+        const double deltaBeta = bl - bh;
+        const bool sw = u < slm_exp(deltaEnergy * deltaBeta);
+        if (m.t == tt + 1) my_src = sw ? tt : cur;
+        if (m.t == tt) { my_swapped = sw; mid_src = sw ? cur : tt; }
+        if (!sw) cur = tt;
+      }
+      if (m.t == 0) my_src = cur;
+      const double lb = slm_log(beta);
+      const double lbh = shfl_d(lb, m.lane + 1 < 32 ? m.lane + 1 : m.lane);
+      mid_e = shfl_d(energy, m.base + mid_src);
+      mid_acc = __shfl_sync(0xffffffffu, accepted, m.base + mid_src);
+      const double new_e = shfl_d(energy, m.base + my_src);
+      const int new_acc = __shfl_sync(0xffffffffu, accepted, m.base + my_src);
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = shfl_d(x[i], m.base + my_src);
+      energy = new_e;
+      accepted = new_acc;
+      if (active && m.t < T - 1) {
+        swap_type = my_swapped ? 1 : 2;
+        double Pb[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Pb[k] = p.p_beta[pidx(p, k, m.t, m.s)];
+        stats_accumulate<1>(Pb, 0.0, 4.0, lb - lbh, lb, my_swapped);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p.p_beta[pidx(p, k, m.t, m.s)] = Pb[k];
+      }
+      if (m.t > 0) beta = s_lad[m.t];
+    }
+
+    if (active) {
+      lg_min_e = smin(lg_min_e, mid_e);
+      lg_accepts += (u32)mid_acc;
+      lg_swaps += (swap_type == 1);
+      lg_att += (swap_type != 0);
+      if (m.t == 0) {
+        const double nn = (double)(r + 1);
+        const double rnn = 1.0 / nn;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const size_t o = (size_t)i * p.n_stacks + m.s;
+          const double mo = p.ep_m[o];
+          const double xi = x[i];
+          const double newM = mo + div_by(xi - mo, nn, rnn);
+          p.ep_s[o] = p.ep_s[o] + (xi - mo) * (xi - newM);
+          p.ep_m[o] = newM;
+        }
+        if (p.rows_out) {
+          double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (D + SLGPU_ROW_EXTRA);
+#pragma unroll
+          for (int i = 0; i < D; ++i) row[i] = x[i];
+          row[D] = energy;
+          row[D + 1] = row_sigma;
+          row[D + 2] = row_beta;
+          row[D + 3] = (double)accepted;
+          row[D + 4] = (double)swap_type;
+        }
+      }
+    }
+  }
+
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) p.x[(size_t)i * C + c] = x[i];
+    p.energy[c] = energy;
+    p.row_sigma[c] = row_sigma;
+    p.row_beta[c] = row_beta;
+    p.sigma[c] = sigma;
+    p.beta[c] = beta;
+    p.nscale[c] = nscale;
+    p.sh_count[c] = sh_count;
+    p.accepted[c] = accepted;
+    p.swap_type[c] = swap_type;
+    p.lg_accepts[c] = lg_accepts;
+    p.lg_swaps[c] = lg_swaps;
+    p.lg_swap_attempts[c] = lg_att;
+    p.lg_min_energy[c] = lg_min_e;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p.p_sig[pidx(p, k, m.t, m.s)] = Ps[k];
+  }
+}
+
+}  // namespace slgpu
+
+#endif

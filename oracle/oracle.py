@@ -36,8 +36,9 @@ class SloConfig(C.Structure):
 def build(force=False):
     src = os.path.join(_HERE, "sl_oracle.cpp")
     hdr = os.path.join(_HERE, "sl_oracle.h")
+    mth = os.path.join(os.path.dirname(_HERE), "include", "slgpu_math.h")
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(mth))):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B", "libsl_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH

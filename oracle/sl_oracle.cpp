@@ -8,10 +8,15 @@
  *
  * Build: g++ -O2 -DNDEBUG -ffp-contract=off -fPIC -shared (oracle/Makefile).  -ffp-contract=off makes
  * every a*b+c two roundings unless std::fma is written out; the CUDA kernels are compiled with
- * -fmad=false and mirror the same explicit fma() calls, so +,-,*,/,sqrt,fma agree bit for bit and
- * only libm transcendentals (exp, log, sin, cos) can differ between the two sides.
+ * -fmad=false and mirror the same explicit fma() calls, so +,-,*,/,sqrt,fma agree bit for bit; exp, log
+ * and sin/cos come from include/slgpu_math.h on both sides, so whole runs agree bit for bit.
  */
 #include "sl_oracle.h"
+
+/* exp / log / sincos: the deterministic fp64 implementations shared with the device code (include/slgpu_math.h,
+ * within 1 ulp of glibc, checked by tests/test_math.py) stand in for the reference's std::exp / std::log
+ * (chainarray.cpp:41,64; sampler.cpp:160; adaptive.cpp:100-139) so that CPU and GPU results are bit-identical. */
+#include "slgpu_math.h"
 
 #include <algorithm>
 #include <array>
@@ -74,10 +79,11 @@ void draw_normals(u64 seed, u32 chain, u64 round, u32 d, double* z) {
   for (u32 k = 0; 2 * k < d; ++k) {
     double ua, ub;
     philox_draw(seed, chain, round, 0, k, ua, ub);
-    const double R = std::sqrt(-2.0 * std::log(ua));
-    const double th = 6.283185307179586476925286766559 * ub;
-    z[2 * k] = R * std::cos(th);
-    if (2 * k + 1 < d) z[2 * k + 1] = R * std::sin(th);
+    const double R = std::sqrt(-2.0 * slm_log(ua));
+    double sn, cs;
+    slm_sincos2pi(ub, &sn, &cs);
+    z[2 * k] = R * cs;
+    if (2 * k + 1 < d) z[2 * k + 1] = R * sn;
   }
 }
 
@@ -332,18 +338,18 @@ struct Regression {
     return model_predict(models[midx(chain)].w, opt, min_cap, max_cap, side);
   }
   /* adaptive.cpp:108-116 */
-  void betaUpdate(u32 chain, double bl, double bh, bool acc) { update(chain, std::log(bl) - std::log(bh), std::log(bl), acc); }
+  void betaUpdate(u32 chain, double bl, double bh, bool acc) { update(chain, slm_log(bl) - slm_log(bh), slm_log(bl), acc); }
   /* adaptive.cpp:118-132; chain = coldest chain of its stack */
   void computeBetaStack(u32 chain) {
     double logbeta = 0.0;
     for (u32 i = 1; i < nTemps; ++i) {
       logbeta -= predict(chain + i - 1, logbeta);
-      values[chain + i] = std::exp(logbeta);
+      values[chain + i] = slm_exp(logbeta);
     }
   }
   /* adaptive.cpp:134-139 */
   double computeSigma(u32 chain, double t) {
-    const double sigma = std::exp(predict(chain, t));
+    const double sigma = slm_exp(predict(chain, t));
     values[chain] = sigma;
     return sigma;
   }
@@ -596,7 +602,7 @@ struct slo_sampler {
   bool accept_proposal(double eNew, double eOld, double beta, double u) const {
     if (std::isinf(eNew)) return false;
     const double deltaEnergy = eNew - eOld;
-    const double p = std::exp(-1.0 * beta * deltaEnergy);
+    const double p = slm_exp(-1.0 * beta * deltaEnergy);
     return u < p;
   }
   /* acceptSwap as called from ChainArray::swap, chainarray.cpp:55-67,171: the call passes
@@ -604,7 +610,7 @@ struct slo_sampler {
   bool accept_swap(double eL, double eH, double bL, double bH, double u) const {
     const double deltaEnergy = eL - eH;
     const double deltaBeta = bL - bH;
-    const double p = std::exp(deltaEnergy * deltaBeta);
+    const double p = slm_exp(deltaEnergy * deltaBeta);
     return u < p;
   }
 
@@ -685,8 +691,8 @@ struct slo_sampler {
     append(id, prop[id], energy, r);
     const Row state = last[id]; /* copy, as the reference takes lastState() by value (sampler.cpp:156) */
     /* sigma adaptation, sampler.cpp:160-162 */
-    const double logtemper = -std::log(state.beta);
-    sigAd.update(id, std::log(state.sigma), logtemper, state.accepted);
+    const double logtemper = -slm_log(state.beta);
+    sigAd.update(id, slm_log(state.sigma), logtemper, state.accepted);
     sigma_[id] = sigAd.computeSigma(id, logtemper);
     /* proposal shape, sampler.cpp:165-166 */
     if (state.accepted) {
@@ -732,7 +738,7 @@ struct slo_sampler {
     ladder[0] = 1.0;
     for (u32 i = 1; i < T; ++i) {
       logbeta -= model_predict(betaAd.models[i - 1].w, betaAd.opt, betaAd.min_cap, betaAd.max_cap, logbeta);
-      ladder[i] = std::exp(logbeta);
+      ladder[i] = slm_exp(logbeta);
     }
   }
   void round_batched() {
@@ -747,10 +753,10 @@ struct slo_sampler {
         const std::vector<double> sample(xp.begin(), xp.end());
         const bool acc = append(id, sample, e, r);
         const Row& row = last[id];
-        const double logtemper = -std::log(row.beta);
-        stats_accumulate(&Psig[((size_t)s * T + t) * 9], sigAd.min_cap, sigAd.max_cap, std::log(row.sigma), logtemper, acc);
+        const double logtemper = -slm_log(row.beta);
+        stats_accumulate(&Psig[((size_t)s * T + t) * 9], sigAd.min_cap, sigAd.max_cap, slm_log(row.sigma), logtemper, acc);
         sigAd.log_window(id, acc);
-        const double sigma = std::exp(model_predict(sigAd.models[t].w, sigAd.opt, sigAd.min_cap, sigAd.max_cap, logtemper));
+        const double sigma = slm_exp(model_predict(sigAd.models[t].w, sigAd.opt, sigAd.min_cap, sigAd.max_cap, logtemper));
         sigAd.values[id] = sigma;
         sigma_[id] = sigma;
         if (acc) {
@@ -767,7 +773,7 @@ struct slo_sampler {
           const bool swapped = swap(id, id + 1, r);
           const double bl = beta_[id], bh = beta_[id + 1];
           stats_accumulate(&Pbeta[((size_t)s * T + t) * 9], betaAd.min_cap, betaAd.max_cap,
-                           std::log(bl) - std::log(bh), std::log(bl), swapped);
+                           slm_log(bl) - slm_log(bh), slm_log(bl), swapped);
           betaAd.log_window(id, swapped);
           log_update(id, last[id]);
         }

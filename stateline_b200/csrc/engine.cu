@@ -91,7 +91,7 @@ struct slgpu_engine {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::vector<void*> allocs;
   slgpu_step_params P{};
-  double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr;
+  double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
   void* d_payload = nullptr;
   double *d_rp_z = nullptr, *d_rp_umh = nullptr, *d_rp_uswap = nullptr, *d_rp_xinit = nullptr;
   bool initialised = false, failed = false;
@@ -373,8 +373,8 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
 
 slgpu_status adapt_point(slgpu_engine* e) {
   const uint32_t T = e->cfg.nTemps;
-  slgpu_tier::k_tier_adapt<<<dim3(T, 2), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_models, e->d_sig_w);
-  slgpu_tier::k_ladder<<<1, 32, 0, e->compute>>>(e->d_models, T, e->cfg.optimalSwapRate, e->d_ladder);
+  slgpu_tier::k_tier_reduce<<<dim3(T, 2, 9), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_sums);
+  slgpu_tier::k_tier_solve<<<1, 64, 0, e->compute>>>(e->d_sums, T, e->d_models, e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
   CU_TRY(cudaGetLastError());
   e->launches += 2;
   return SLGPU_OK;
@@ -499,7 +499,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     P.mn = d_mn; P.mx = d_mx; P.n0_diag = d_n0; P.initial = d_init;
     const size_t nL = (size_t)d * (d + 1) / 2;
     TRY_ST(dev_alloc(e, &P.x, d * C));
-    TRY_ST(dev_alloc(e, &P.L, nL * C));
+    TRY_ST(dev_alloc(e, &P.L, nL * ((C + SLGPU_L_TILE - 1) / SLGPU_L_TILE) * SLGPU_L_TILE));
     TRY_ST(dev_alloc(e, &P.energy, C)); TRY_ST(dev_alloc(e, &P.row_sigma, C)); TRY_ST(dev_alloc(e, &P.row_beta, C));
     TRY_ST(dev_alloc(e, &P.sigma, C)); TRY_ST(dev_alloc(e, &P.beta, C)); TRY_ST(dev_alloc(e, &P.nscale, C));
     TRY_ST(dev_alloc(e, &P.sh_count, C));
@@ -511,6 +511,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     TRY_ST(dev_alloc(e, &e->d_models, (size_t)2 * T * slgpu_tier::kModelStride));
     TRY_ST(dev_alloc(e, &e->d_sig_w, (size_t)3 * T));
     TRY_ST(dev_alloc(e, &e->d_ladder, T));
+    TRY_ST(dev_alloc(e, &e->d_sums, (size_t)2 * T * 9));
     P.sig_w = e->d_sig_w;
     P.ladder = e->d_ladder;
     if (payload && payload_bytes) {
@@ -801,7 +802,8 @@ slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double
   if ((st = sync_all(e)) != SLGPU_OK) return st;
   const size_t C = e->C, d = e->cfg.nDims, nL = d * (d + 1) / 2;
   std::vector<double> packed(nL);
-  CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), e->P.L + chain, C * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
+  const double* lsrc = e->P.L + (size_t)(chain / SLGPU_L_TILE) * nL * SLGPU_L_TILE + chain % SLGPU_L_TILE;
+  CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), lsrc, SLGPU_L_TILE * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
   double cnt = 0.0, ns = 0.0;
   CU_TRY(cudaMemcpy(&cnt, e->P.sh_count + chain, sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(&ns, e->P.nscale + chain, sizeof(double), cudaMemcpyDeviceToHost));

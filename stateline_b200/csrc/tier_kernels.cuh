@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "slgpu_math.h"
+
 namespace slgpu_tier {
 
 constexpr int kModelStride = 16;  // mu_xx[9], mu_xy[3], w[3], count
@@ -132,7 +134,7 @@ __device__ inline void compute_ladder(const double* beta_models, uint32_t T, dou
   ladder[0] = 1.0;
   for (uint32_t i = 1; i < T; ++i) {
     logbeta -= model_predict(beta_models + (size_t)(i - 1) * kModelStride + 12, opt_swap, kBetaMinCap, kBetaMaxCap, logbeta);
-    ladder[i] = exp(logbeta);
+    ladder[i] = slm_exp(logbeta);
   }
 }
 
@@ -148,40 +150,40 @@ __global__ void k_tier_init(double* models, double* sig_w, double* ladder, uint3
   if (t == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
 }
 
-// grid (T, 2), 256 threads: block (t, which) sums the 9 statistics of tier t over the stacks, clears
-// them, and folds them into the model.
-__global__ void __launch_bounds__(256) k_tier_adapt(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* models, double* sig_w) {
-  const uint32_t t = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
-  double* P = which ? p_beta : p_sig;
-  const size_t C = (size_t)S * T;
+// Statistics layout: P[(k * T + t) * S + s], k < 9 (coalesced over the stacks of a tier).
+// grid (T, 2, 9), 256 threads: block (t, which, k) sums statistic k of tier t over the stacks in the
+// fixed shape of the oracle's reduce_tree256 (slot i adds stacks i, i+256, ... in order, then a halving
+// tree), clears it, and writes sums[(which * T + t) * 9 + k].
+__global__ void __launch_bounds__(256) k_tier_reduce(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* sums) {
+  const uint32_t t = blockIdx.x, which = blockIdx.y, k = blockIdx.z, tid = threadIdx.x;
+  double* P = (which ? p_beta : p_sig) + ((size_t)k * T + t) * S;
   __shared__ double a[256];
-  __shared__ double Pk[9];
-  for (int k = 0; k < 9; ++k) {
-    double acc = 0.0;
-    for (uint32_t m = tid; m < S; m += 256) {
-      const size_t idx = (size_t)k * C + (size_t)m * T + t;
-      acc += P[idx];
-      P[idx] = 0.0;
-    }
-    a[tid] = acc;
-    __syncthreads();
-    for (uint32_t s = 128; s > 0; s >>= 1) {
-      if (tid < s) a[tid] += a[tid + s];
-      __syncthreads();
-    }
-    if (tid == 0) Pk[k] = a[0];
+  double acc = 0.0;
+  for (uint32_t m = tid; m < S; m += 256) {
+    acc += P[m];
+    P[m] = 0.0;
+  }
+  a[tid] = acc;
+  __syncthreads();
+  for (uint32_t s = 128; s > 0; s >>= 1) {
+    if (tid < s) a[tid] += a[tid + s];
     __syncthreads();
   }
-  if (tid == 0) {
-    double* m = models + (size_t)(which * T + t) * kModelStride;
-    model_update_batched(m, Pk);
-    if (which == 0)
-      for (int i = 0; i < 3; ++i) sig_w[3 * t + i] = m[12 + i];
-  }
+  if (tid == 0) sums[(size_t)(which * T + t) * 9 + k] = a[0];
 }
 
-__global__ void k_ladder(const double* models, uint32_t T, double opt_swap, double* ladder) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
+// one block, >= 2T threads: thread (which, t) folds the summed statistics into its model and re-solves;
+// then thread 0 rebuilds the ladder.
+__global__ void k_tier_solve(const double* sums, uint32_t T, double* models, double* sig_w, double opt_swap, double* ladder) {
+  const uint32_t i = threadIdx.x;
+  if (i < 2 * T) {
+    double* m = models + (size_t)i * kModelStride;
+    model_update_batched(m, sums + (size_t)i * 9);
+    if (i < T)
+      for (int j = 0; j < 3; ++j) sig_w[3 * i + j] = m[12 + j];
+  }
+  __syncthreads();
+  if (i == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
 }
 
 }  // namespace slgpu_tier

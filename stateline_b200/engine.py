@@ -150,7 +150,7 @@ class Engine:
         text = config if isinstance(config, str) else json.dumps(config)
         if plugin is None or plugin in BUILTIN_ENTRIES:
             entry = BUILTIN_ENTRIES[plugin or "demo_gauss"]
-            plugin = _build.build_targets()
+            plugin = os.environ.get("SLGPU_TARGETS_SO") or _build.build_targets()  # env: development A/B builds
         pl = None
         n = 0
         if payload is not None:

@@ -39,6 +39,8 @@ struct DoubleWell {
 struct GaussFact {
   const double* prm;
   __device__ explicit GaussFact(const void* payload) : prm((const double*)payload) {}
+  template <int D>
+  static constexpr int static_job_types() { return (D + 1) / 2; }
   __device__ double operator()(u32 job, const double* x, u32 d) const {
     const double* mu = prm;
     const double* is = prm + d;
