@@ -243,6 +243,7 @@ def main():
         for _ in range(K):
             e.step_rounds(R)
         ms = e.timer_stop()
+        step_kernel_ms, step_kernel_n = e.timer_step_kernel()
         e.sync()
         barrier()
         clocks = sampler.finish()
@@ -301,24 +302,27 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fp64_peak = measure_fp64_peak(local_rank)
-    # the step kernel is the whole timed region bar the two tiny tier kernels per step (see profiles/)
-    step_launch_ms = ms / K
+    # the dominant kernel is pt_step (one launch per step); its launches carry their own event pairs
+    step_launch_ms = step_kernel_ms / max(step_kernel_n, 1)
     per_gpu_steps_per_launch = S * T * R
     achieved_tf = FLOPS_PER_CHAIN_STEP * per_gpu_steps_per_launch / (step_launch_ms * 1e-3) / 1e12
     alg_bytes = algorithmic_bytes_per_chain_step(d, T, R) * per_gpu_steps_per_launch
+    achieved_gbs = alg_bytes / (step_launch_ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "pt_step_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-        "traffic": traffic, "peak_source": "measured live: register-resident DFMA loop (slgpu_measure_fp64_peak)",
-        "flops_per_chain_step": FLOPS_PER_CHAIN_STEP, "chain_steps_per_launch": per_gpu_steps_per_launch,
-        "kernel": "pt_step_kernel<GaussFact,20>", "launch_ms": step_launch_ms,
-        "hbm": {"bound": "hbm", "achieved": alg_bytes / (step_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (step_launch_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": hbm_src},
+        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+        "traffic": traffic, "peak_source": hbm_src, "kernel": "pt_step_fast_kernel<GaussFact,20,128>",
+        "launch_ms": step_launch_ms, "launches_timed": int(step_kernel_n), "share_of_step": step_kernel_ms / ms,
+        "algorithmic_bytes_per_launch": alg_bytes, "chain_steps_per_launch": per_gpu_steps_per_launch,
+        "bytes_per_chain_step": algorithmic_bytes_per_chain_step(d, T, R),
+        "note": "latency-bound in round 1: neither roof is close (DESIGN.md section 5, profiles/README.md)",
+        "fp64": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+                 "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
+                 "peak_source": "measured live: register-resident DFMA loop (slgpu_measure_fp64_peak)"},
     }
 
     out = {

@@ -103,6 +103,8 @@ uint64_t slgpu_rows_emitted(const slgpu_engine* e); /* rows produced on the devi
 slgpu_status slgpu_timer_start(slgpu_engine* e);
 slgpu_status slgpu_timer_stop(slgpu_engine* e, double* elapsed_ms); /* waits for the stop event */
 uint64_t slgpu_launch_count(const slgpu_engine* e);                 /* kernels launched so far */
+/* of the last timed region: summed device time of the step-kernel launches alone (their own event pairs) */
+slgpu_status slgpu_timer_step_kernel(slgpu_engine* e, double* total_ms, uint64_t* n_launches);
 
 /* ---- state inspection (synchronises) ---- */
 uint32_t slgpu_n_dims(const slgpu_engine* e);

@@ -89,6 +89,10 @@ struct slgpu_engine {
   const slgpu_plugin_v1* plug = nullptr;
   cudaStream_t compute = nullptr, drain = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool timing = false;                 // between slgpu_timer_start and slgpu_timer_stop
+  std::vector<cudaEvent_t> step_ev;    // (start, stop) pairs around every step-kernel launch of the timed region
+  double step_kernel_ms = 0.0;
+  uint64_t step_kernel_launches = 0;
   std::vector<void*> allocs;
   slgpu_step_params P{};
   double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
@@ -352,7 +356,18 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
   }
   e->P.round_begin = e->rounds_done;
   e->P.n_rounds = n;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e->timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, e->compute);
+  }
   const int rc = e->plug->launch_step(&e->P, (void*)e->compute);
+  if (e->timing) {
+    cudaEventRecord(ev1, e->compute);
+    e->step_ev.push_back(ev0);
+    e->step_ev.push_back(ev1);
+  }
   if (rc != 0) {
     e->failed = true;
     return fail(SLGPU_E_CUDA, std::string("launch_step: ") + cudaGetErrorString((cudaError_t)rc));
@@ -701,6 +716,13 @@ slgpu_status slgpu_run(slgpu_engine* e) {
 uint64_t slgpu_rounds_done(const slgpu_engine* e) { return e ? e->rounds_done : 0; }
 uint64_t slgpu_rows_emitted(const slgpu_engine* e) { return e ? e->rows_emitted : 0; }
 uint64_t slgpu_launch_count(const slgpu_engine* e) { return e ? e->launches : 0; }
+
+slgpu_status slgpu_timer_step_kernel(slgpu_engine* e, double* total_ms, uint64_t* n_launches) {
+  if (!e || !total_ms || !n_launches) return fail(SLGPU_E_ARG, "NULL argument");
+  *total_ms = e->step_kernel_ms;
+  *n_launches = e->step_kernel_launches;
+  return SLGPU_OK;
+}
 uint32_t slgpu_n_dims(const slgpu_engine* e) { return e ? e->cfg.nDims : 0; }
 uint32_t slgpu_n_chains(const slgpu_engine* e) { return e ? (uint32_t)e->C : 0; }
 
@@ -749,6 +771,9 @@ slgpu_status slgpu_advance(slgpu_engine* e, size_t n_rows) {
 slgpu_status slgpu_timer_start(slgpu_engine* e) {
   slgpu_status st = check_ready(e, false);
   if (st != SLGPU_OK) return st;
+  for (cudaEvent_t ev : e->step_ev) cudaEventDestroy(ev);
+  e->step_ev.clear();
+  e->timing = true;
   CU_TRY(cudaEventRecord(e->t0, e->compute));
   return SLGPU_OK;
 }
@@ -762,6 +787,15 @@ slgpu_status slgpu_timer_stop(slgpu_engine* e, double* elapsed_ms) {
   float ms = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms, e->t0, e->t1));
   *elapsed_ms = ms;
+  e->timing = false;
+  e->step_kernel_ms = 0.0;
+  e->step_kernel_launches = e->step_ev.size() / 2;
+  for (size_t i = 0; i + 1 < e->step_ev.size(); i += 2) {
+    float k = 0.f;
+    if (cudaEventElapsedTime(&k, e->step_ev[i], e->step_ev[i + 1]) == cudaSuccess) e->step_kernel_ms += k;
+  }
+  for (cudaEvent_t ev : e->step_ev) cudaEventDestroy(ev);
+  e->step_ev.clear();
   return SLGPU_OK;
 }
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "slgpu_last_error", "slgpu_version", "slgpu_create", "slgpu_destroy", "slgpu_set_replay",
     "slgpu_init_chains", "slgpu_step_rounds", "slgpu_sync", "slgpu_run", "slgpu_rounds_done",
     "slgpu_drain", "slgpu_peek", "slgpu_advance", "slgpu_rows_emitted", "slgpu_timer_start",
-    "slgpu_timer_stop", "slgpu_launch_count", "slgpu_n_dims", "slgpu_n_chains", "slgpu_get_last_rows",
+    "slgpu_timer_stop", "slgpu_timer_step_kernel", "slgpu_launch_count", "slgpu_n_dims", "slgpu_n_chains", "slgpu_get_last_rows",
     "slgpu_get_sigma_beta", "slgpu_get_shaper", "slgpu_get_models", "slgpu_get_ladder",
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
@@ -75,6 +75,7 @@ def lib():
     L.slgpu_rows_emitted.restype = C.c_uint64
     L.slgpu_timer_start.argtypes = [C.c_void_p]
     L.slgpu_timer_stop.argtypes = [C.c_void_p, _dp]
+    L.slgpu_timer_step_kernel.argtypes = [C.c_void_p, _dp, _u64p]
     L.slgpu_launch_count.argtypes = [C.c_void_p]
     L.slgpu_launch_count.restype = C.c_uint64
     L.slgpu_n_dims.argtypes = [C.c_void_p]
@@ -223,6 +224,12 @@ class Engine:
         ms = C.c_double()
         _check(lib().slgpu_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def timer_step_kernel(self):
+        """(summed ms, launches) of the step-kernel launches inside the last timed region."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().slgpu_timer_step_kernel(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # ---- cold rows
     def drain(self, max_rows=None):

@@ -23,6 +23,8 @@ def oracle_for(w, schedule=O.SCHED_BATCHED, rng_mode=O.RNG_PHILOX, seed=1234, st
 
 
 def engine_for(w, rng="philox", seed=1234, sink="host", stack_offset=0, **gpu):
+    if sink == "host":
+        gpu.setdefault("hostRingRounds", 1024)  # the tests drain at the end
     cfg = configs.engine_config(w, rng=rng, seed=seed, sink=sink, stackOffset=stack_offset, **gpu)
     return Engine(cfg, plugin=w["plugin"], payload=w["payload"])
 
