@@ -165,7 +165,8 @@ def test_bench_size_properties():
         assert np.all(sig > 0) and np.all(sig <= np.exp(4.0) * (1 + 1e-15))
         c = eng.counters()
         assert np.all(c["length"] == 40) and np.all(c["accepts"] <= 40)
-        assert np.all(c["swap_attempts"].reshape(S, T)[:, :T - 1] == 1 + 4) and  # rounds 8, 18, 28, 38 np.all(c["swap_attempts"].reshape(S, T)[:, T - 1] == 1)
+        assert np.all(c["swap_attempts"].reshape(S, T)[:, :T - 1] == 1 + 4)  # swap rounds 8, 18, 28, 38
+        assert np.all(c["swap_attempts"].reshape(S, T)[:, T - 1] == 1)
         r = eng.rhat()
         assert np.all(np.isfinite(r))
         summ = eng.summary()
