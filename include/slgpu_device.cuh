@@ -573,7 +573,11 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
   if constexpr (D > 0 && D <= 32) {
     if (step_variant() != 3) {
       constexpr int NT = SLGPU_FAST_THREADS;
-      pt_step_fast_kernel<Lik, D, NT><<<grid_for(p, NT), NT, 0, (cudaStream_t)stream>>>(*p);
+      auto kern = pt_step_fast_kernel<Lik, D, NT>;
+      const size_t smem = fast_smem_bytes<D, NT>(p->n_temps);
+      static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<D, NT>(1));
+      if (attr != cudaSuccess) return (int)attr;
+      kern<<<grid_for(p, NT), NT, smem, (cudaStream_t)stream>>>(*p);
       return (int)cudaGetLastError();
     }
   }

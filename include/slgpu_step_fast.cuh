@@ -37,8 +37,11 @@ __device__ __forceinline__ double div_by(double n, double c, double rc) {
 #ifndef SLGPU_FAST_THREADS
 #define SLGPU_FAST_THREADS 128
 #endif
+#ifndef SLGPU_FAST_SMEM_PAD
+#define SLGPU_FAST_SMEM_PAD 0 /* development knob: extra dynamic shared memory to cap the blocks per SM */
+#endif
 #ifndef SLGPU_COLBLOCK
-#define SLGPU_COLBLOCK 4
+#define SLGPU_COLBLOCK 2
 #endif
 
 constexpr int kLs = (int)SLGPU_L_TILE; /* doubles between consecutive packed entries of a chain's L */
@@ -47,105 +50,128 @@ constexpr int kColBlock = SLGPU_COLBLOCK; /* columns per block of the blocked tr
 /* Columns K0..K0+KB-1 of the proposal GEMV: a_j = fma(N_jk, z_k, a_j) for j >= k.  Rows j >= K0 are
  * loaded unconditionally (for K0 <= j < k the address is still inside the packed triangle, the value is
  * ignored), so a column's loads issue back to back; only the first KB rows need the j >= k guard. */
+template <int D, int K0, int K1>
+__device__ __forceinline__ void gemv_col(int k, const double* col, double zk, double n0k, double nscale, bool fresh, double* a) {
+#pragma unroll
+  for (int j = K0; j < D; ++j) {
+    if (j >= K1 || j >= k) { /* static for j >= K1, warp-uniform otherwise */
+      double njk = col[j] * nscale;
+      if (j < K1 && j == k) njk = fresh ? n0k : njk + 1e-4;
+      a[j] = fma(njk, zk, a[j]);
+    }
+  }
+}
+
 template <int D, int K0, int KB>
 __device__ __forceinline__ void gemv_block(const double* Lc, const double* zs, int zstride, double nscale, bool fresh,
                                            const double* s_n0, double* a) {
   constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
 #pragma unroll 1
-  for (int k = K0; k < K1; ++k) {
-    const double zk = zs[k * zstride];
+  for (int k = K0; k < K1; k += 2) { /* two columns per trip: both columns' loads are in flight together */
+    const bool two = (k + 1 < K1);
     const double* Lk = Lc + k * kLs;
-    double col[D];
+    double col0[D], col1[D];
 #pragma unroll
-    for (int j = K0; j < D; ++j) col[j] = Lk[(j * (j + 1) / 2) * kLs];
-    const double n0k = s_n0[k];
+    for (int j = K0; j < D; ++j) col0[j] = Lk[(j * (j + 1) / 2) * kLs];
+    if (two) {
 #pragma unroll
-    for (int j = K0; j < D; ++j) {
-      if (j >= K1 || j >= k) { /* static for j >= K1, warp-uniform otherwise */
-        double njk = col[j] * nscale;
-        if (j < K1 && j == k) njk = fresh ? n0k : njk + 1e-4;
-        a[j] = fma(njk, zk, a[j]);
-      }
+      for (int j = K0; j < D; ++j) col1[j] = Lk[(j * (j + 1) / 2 + 1) * kLs];
     }
+    gemv_col<D, K0, K1>(k, col0, zs[k * zstride], s_n0[k], nscale, fresh, a);
+    if (two) gemv_col<D, K0, K1>(k + 1, col1, zs[(k + 1) * zstride], s_n0[k + 1], nscale, fresh, a);
   }
   if constexpr (K1 < D) gemv_block<D, K1, KB>(Lc, zs, zstride, nscale, fresh, s_n0, a);
 }
 
-/* Columns K0..K0+KB-1 of ProposalShaper::update's rank-1 sweep (src/infer/adaptive.cpp:184-197). */
-template <int D, int K0, int KB>
-__device__ __forceinline__ void shaper_block(double* Lc, double scale, double* xs, double* fr, double& xk, double* diag,
-                                             int dstride) {
-  constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
+/* Columns K0..K0+KB-1 of ProposalShaper::update's rank-1 sweep (src/infer/adaptive.cpp:184-197).
+ * xs (the scaled jump) and fr (row sums of squares) live in shared memory, one column per staged chain:
+ * xs[j*xst], fr[j*fst].  They are indexed by the rolled column counter k there, which a register array
+ * cannot be, and phase B then needs few enough registers for 12 warps per SM. */
+template <int D, int K0, int K1>
+__device__ __forceinline__ void shaper_col(int k, double* Lk, const double* col, double scale, double* xs, int xst, double* fr, int fst) {
   const double eps = 1e-18;
-#pragma unroll 1
-  for (int k = K0; k < K1; ++k) {
-    double* Lk = Lc + k * kLs; /* column k: L(j,k) = Lk[(j(j+1)/2)*ls] */
-    double col[D];
+  const double xk = xs[k * xst];
+  double Lkk = col[K0];
 #pragma unroll
-    for (int j = K0; j < D; ++j) col[j] = Lk[(j * (j + 1) / 2) * kLs];
-    double Lkk = col[K0];
+  for (int j = K0 + 1; j < K1; ++j) Lkk = (j == k) ? col[j] : Lkk;
+  Lkk = Lkk * scale;
+  const double V = smax(eps, Lkk);
+  const double rV = 1.0 / V;
+  const double r = sqrt(V * V + xk * xk);
+  const double c = div_by(r, V, rV);
+  const double s = div_by(xk, V, rV);
+  const double rc = 1.0 / c;
+  Lk[(k * (k + 1) / 2) * kLs] = r;
+  fr[k * fst] = fma(r, r, fr[k * fst]); /* the diagonal closes row k's sum */
 #pragma unroll
-    for (int j = K0 + 1; j < K1; ++j) Lkk = (j == k) ? col[j] : Lkk;
-    Lkk = Lkk * scale;
-    const double V = smax(eps, Lkk);
-    const double rV = 1.0 / V;
-    const double r = sqrt(V * V + xk * xk);
-    const double c = div_by(r, V, rV);
-    const double s = div_by(xk, V, rV);
-    const double rc = 1.0 / c;
-    Lk[(k * (k + 1) / 2) * kLs] = r;
-    diag[k * dstride] = r;
-    double xnext = 0.0;
-#pragma unroll
-    for (int j = K0 + 1; j < D; ++j) {
-      if (j >= K1 || j > k) { /* static for j >= K1, warp-uniform otherwise */
-        double Ljk = col[j] * scale;
-        Ljk = div_by(Ljk + s * xs[j], c, rc);
-        Lk[(j * (j + 1) / 2) * kLs] = Ljk;
-        xs[j] = c * xs[j] - s * Ljk;
-        fr[j] = fma(Ljk, Ljk, fr[j]);
-        if (j <= K1) xnext = (j == k + 1) ? xs[j] : xnext;
-      }
+  for (int j = K0 + 1; j < D; ++j) {
+    if (j >= K1 || j > k) { /* static for j >= K1, warp-uniform otherwise */
+      const double xj = xs[j * xst];
+      double Ljk = col[j] * scale;
+      Ljk = div_by(Ljk + s * xj, c, rc);
+      Lk[(j * (j + 1) / 2) * kLs] = Ljk;
+      xs[j * xst] = c * xj - s * Ljk;
+      fr[j * fst] = fma(Ljk, Ljk, fr[j * fst]);
     }
-    xk = xnext;
   }
-  if constexpr (K1 < D) shaper_block<D, K1, KB>(Lc, scale, xs, fr, xk, diag, dstride);
+}
+
+template <int D, int K0, int KB>
+__device__ __forceinline__ void shaper_block(double* Lc, double scale, double* xs, int xst, double* fr, int fst) {
+  constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
+#pragma unroll 1
+  for (int k = K0; k < K1; k += 2) { /* two columns per trip; column k's stores never touch column k+1 */
+    const bool two = (k + 1 < K1);
+    double* Lk = Lc + k * kLs; /* column k: L(j,k) = Lk[(j(j+1)/2)*ls] */
+    double col0[D], col1[D];
+#pragma unroll
+    for (int j = K0; j < D; ++j) col0[j] = Lk[(j * (j + 1) / 2) * kLs];
+    if (two) {
+#pragma unroll
+      for (int j = K0; j < D; ++j) col1[j] = Lk[(j * (j + 1) / 2 + 1) * kLs];
+    }
+    shaper_col<D, K0, K1>(k, Lk, col0, scale, xs, xst, fr, fst);
+    if (two) shaper_col<D, K0, K1>(k + 1, Lk + kLs, col1, scale, xs, xst, fr, fst);
+  }
+  if constexpr (K1 < D) shaper_block<D, K1, KB>(Lc, scale, xs, xst, fr, fst);
 }
 
 /* ProposalShaper::update (src/infer/adaptive.cpp:173-209), blocked column sweep; Lc[(r(r+1)/2+k)*ls].
- * diag[k*dstride] is scratch (shared memory) for the new diagonal, so no register array is indexed by k. */
+ * On entry xs[j*xst] holds the accepted jump; fr[j*fst] is scratch. */
 template <int D>
-__device__ __forceinline__ double shaper_update_rolled(double* Lc, double* xs, double count, double prop_norm,
-                                                        double* diag, int dstride) {
+__device__ __forceinline__ double shaper_update_rolled(double* Lc, double* xs, int xst, double* fr, int fst, double count,
+                                                        double prop_norm) {
   const double eps = 1e-18;
   const double sq = sqrt(count);
   const double rsq = 1.0 / sq;
   const double scale = sqrt((count - 1.0) / count);
-  double fr[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    xs[i] = div_by(xs[i], sq, rsq);
-    fr[i] = 0.0;
+    xs[i * xst] = div_by(xs[i * xst], sq, rsq);
+    fr[i * fst] = 0.0;
   }
-  double xk = xs[0];
-  shaper_block<D, 0, kColBlock>(Lc, scale, xs, fr, xk, diag, dstride);
-  /* the diagonal is the last entry of each row sum */
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    const double dj = diag[j * dstride];
-    fr[j] = fma(dj, dj, fr[j]);
-  }
+  shaper_block<D, 0, kColBlock>(Lc, scale, xs, xst, fr, fst);
   /* |L|_F: slot l = row sum l (D <= 32), halving tree over 32 slots; slots >= D are +0 and are skipped */
+  double f[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) f[j] = fr[j * fst];
   int nlive = D;
 #pragma unroll
   for (int mm = 16; mm > 0; mm >>= 1) {
 #pragma unroll
     for (int l = 0; l < mm; ++l)
-      if (l + mm < D && l + mm < nlive) fr[l] += fr[l + mm];
+      if (l + mm < D && l + mm < nlive) f[l] += f[l + mm];
     if (nlive > mm) nlive = mm;
   }
-  const double frob = sqrt(fr[0]);
+  const double frob = sqrt(f[0]);
   return prop_norm / smax(frob, eps);
+}
+
+/* dynamic shared memory of pt_step_fast_kernel */
+template <int D, int NT>
+inline size_t fast_smem_bytes(unsigned n_temps) {
+  const size_t nsb = (size_t)(NT / 32) * (32u / n_temps);
+  return ((size_t)3 * D * NT + (size_t)2 * D * nsb) * sizeof(double) + SLGPU_FAST_SMEM_PAD;
 }
 
 template <class Lik, int D, int NT>
@@ -161,8 +187,15 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 
   __shared__ double s_mn[D], s_mx[D], s_n0[D];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
-  __shared__ double s_jump[D * NT]; /* staged accepted jumps, [i][slot] */
-  __shared__ double s_z[D * NT];    /* this round's normals, [k][thread] */
+  /* dynamic shared memory (see fast_smem_bytes): three [D][NT] panels + the EPSR state of the block's stacks */
+  extern __shared__ double s_dyn[];
+  double* const s_jump = s_dyn;              /* staged accepted jumps, [i][slot] */
+  double* const s_z = s_dyn + D * NT;        /* this round's normals, [k][thread] */
+  double* const s_x = s_dyn + 2 * D * NT;    /* current sample of every chain of the block, [i][thread] */
+  const int nsb = (NT / 32) * m.spw;         /* stacks per block */
+  double* const s_epm = s_dyn + 3 * D * NT;  /* EPSRDiagnostic M, [i][stack of block] */
+  double* const s_eps = s_epm + D * nsb;     /* EPSRDiagnostic S */
+  const int sb = (tid >> 5) * m.spw + m.sl;  /* this thread's stack within the block */
   __shared__ double s_cnt[NT];      /* shaper count (already incremented) of the staged chain */
   __shared__ double s_nsc[NT];      /* result: new N scale, indexed by owning thread */
   __shared__ u32 s_chain[NT];       /* chain id of the staged chain */
@@ -184,9 +217,15 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 
   const Lik lik(p.payload);
   const double* Lc = l_base(p.L, c, D * (D + 1) / 2); /* rewritten by other threads in phase B: no __restrict__ */
-  double x[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) x[i] = p.x[(size_t)i * C + c];
+  for (int i = 0; i < D; ++i) s_x[i * NT + tid] = p.x[(size_t)i * C + c];
+  if (active && m.t == 0) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      s_epm[i * nsb + sb] = p.ep_m[(size_t)i * p.n_stacks + m.s];
+      s_eps[i * nsb + sb] = p.ep_s[(size_t)i * p.n_stacks + m.s];
+    }
+  }
   double Ps[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) Ps[k] = active ? p.p_sig[pidx(p, k, m.t, m.s)] : 0.0;
@@ -230,7 +269,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       /* GaussianProposal::propose (sampler.cpp:79-88): a_i = sum_{k<=i} fma(N_ik, z_k, .), k ascending */
       gemv_block<D, 0, kColBlock>(Lc, s_z + tid, NT, nscale, fresh, s_n0, a);
 #pragma unroll
-      for (int i = 0; i < D; ++i) a[i] = bounce1(x[i] + a[i] * sigma, s_mn[i], s_mx[i]);
+      for (int i = 0; i < D; ++i) a[i] = bounce1(s_x[i * NT + tid] + a[i] * sigma, s_mn[i], s_mx[i]);
       /* energy = sum over job types in order (sampler.cpp:148-150) */
       double e_new = 0.0;
       if constexpr (StaticJobs<Lik, D>::value > 0) {
@@ -253,8 +292,8 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           const double nx = a[i];
-          s_jump[i * NT + slot] = nx - x[i]; /* the accepted jump (sampler.cpp:166) */
-          x[i] = nx;
+          s_jump[i * NT + slot] = nx - s_x[i * NT + tid]; /* the accepted jump (sampler.cpp:166) */
+          s_x[i * NT + tid] = nx;
         }
         s_cnt[slot] = sh_count;
         s_chain[slot] = c;
@@ -270,9 +309,6 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
       sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
     }
-    /* park x in this thread's (now dead) column of s_z while phase B needs the registers */
-#pragma unroll
-    for (int i = 0; i < D; ++i) s_z[i * NT + tid] = x[i];
     __syncthreads();
     /* ================= phase B: compacted ProposalShaper updates ================= */
     {
@@ -280,17 +316,13 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       /* slot -> thread map that spreads the staged chains over all warps (lane-major): with few warps
        * resident per SM, parallel half-empty warps beat one full warp */
       const int slot = (tid & 31) * (NT / 32) + (tid >> 5);
-      if (slot < nacc) {
-        double xs[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) xs[i] = s_jump[i * NT + slot];
-        s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), xs, s_cnt[slot], p.prop_norm, s_jump + slot, NT);
+      if (slot < nacc) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
+        s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
+                                                       s_cnt[slot], p.prop_norm);
       }
       if (tid == 0) s_nacc[par ^ 1] = 0;
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = s_z[i * NT + tid];
     if (acc) nscale = s_nsc[tid];
 
     /* ================= swap sweep, hottest pair first ================= */
@@ -325,8 +357,16 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       mid_acc = __shfl_sync(0xffffffffu, accepted, m.base + mid_src);
       const double new_e = shfl_d(energy, m.base + my_src);
       const int new_acc = __shfl_sync(0xffffffffu, accepted, m.base + my_src);
+      { /* gather the sample from the source chain's column of s_x (same warp) */
+        const int src_tid = (tid & ~31) + ((m.base + my_src) & 31);
+        double g[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) x[i] = shfl_d(x[i], m.base + my_src);
+        for (int i = 0; i < D; ++i) g[i] = s_x[i * NT + src_tid];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < D; ++i) s_x[i * NT + tid] = g[i];
+        __syncwarp();
+      }
       energy = new_e;
       accepted = new_acc;
       if (active && m.t < T - 1) {
@@ -351,17 +391,17 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
         const double rnn = 1.0 / nn;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          const size_t o = (size_t)i * p.n_stacks + m.s;
-          const double mo = p.ep_m[o];
-          const double xi = x[i];
+          const int o = i * nsb + sb;
+          const double mo = s_epm[o];
+          const double xi = s_x[i * NT + tid];
           const double newM = mo + div_by(xi - mo, nn, rnn);
-          p.ep_s[o] = p.ep_s[o] + (xi - mo) * (xi - newM);
-          p.ep_m[o] = newM;
+          s_eps[o] = s_eps[o] + (xi - mo) * (xi - newM);
+          s_epm[o] = newM;
         }
         if (p.rows_out) {
           double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (D + SLGPU_ROW_EXTRA);
 #pragma unroll
-          for (int i = 0; i < D; ++i) row[i] = x[i];
+          for (int i = 0; i < D; ++i) row[i] = s_x[i * NT + tid];
           row[D] = energy;
           row[D + 1] = row_sigma;
           row[D + 2] = row_beta;
@@ -374,7 +414,14 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 
   if (active) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) p.x[(size_t)i * C + c] = x[i];
+    for (int i = 0; i < D; ++i) p.x[(size_t)i * C + c] = s_x[i * NT + tid];
+    if (m.t == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        p.ep_m[(size_t)i * p.n_stacks + m.s] = s_epm[i * nsb + sb];
+        p.ep_s[(size_t)i * p.n_stacks + m.s] = s_eps[i * nsb + sb];
+      }
+    }
     p.energy[c] = energy;
     p.row_sigma[c] = row_sigma;
     p.row_beta[c] = row_beta;
