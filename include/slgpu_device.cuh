@@ -43,13 +43,17 @@
 #define SLGPU_THREADS 128
 #endif
 
+#ifndef SLGPU_PHILOX_INLINE
+#define SLGPU_PHILOX_INLINE __forceinline__
+#endif
+
 namespace slgpu {
 
 typedef unsigned long long u64;
 typedef uint32_t u32;
 
 /* ---- Philox4x32-10, counter layout of the oracle (oracle/sl_oracle.cpp philox_draw) ---- */
-__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4]) {
+__device__ SLGPU_PHILOX_INLINE void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;

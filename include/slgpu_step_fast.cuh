@@ -40,11 +40,15 @@ __device__ __forceinline__ double div_by(double n, double c, double rc) {
 #ifndef SLGPU_FAST_SMEM_PAD
 #define SLGPU_FAST_SMEM_PAD 0 /* development knob: extra dynamic shared memory to cap the blocks per SM */
 #endif
+#ifndef SLGPU_NORMALS_UNROLL
+#define SLGPU_NORMALS_UNROLL 1
+#endif
 #ifndef SLGPU_COLBLOCK
 #define SLGPU_COLBLOCK 2
 #endif
 
 constexpr int kLs = (int)SLGPU_L_TILE; /* doubles between consecutive packed entries of a chain's L */
+constexpr int kNormalsUnroll = SLGPU_NORMALS_UNROLL;
 constexpr int kColBlock = SLGPU_COLBLOCK; /* columns per block of the blocked triangular sweeps */
 
 /* Columns K0..K0+KB-1 of the proposal GEMV: a_j = fma(N_jk, z_k, a_j) for j >= k.  Rows j >= K0 are
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #pragma unroll
       for (int i = 0; i < D; ++i) a[i] = 0.0;
       /* the round's normals go to this thread's column of s_z (rolled loop: one copy of the generator) */
-#pragma unroll 1
+#pragma unroll kNormalsUnroll
       for (int kp = 0; kp < (D + 1) / 2; ++kp) {
         double z0, z1 = 0.0;
         if (replay) {
@@ -313,10 +317,17 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     /* ================= phase B: compacted ProposalShaper updates ================= */
     {
       const int nacc = s_nacc[par];
-      /* slot -> thread map that spreads the staged chains over all warps (lane-major): with few warps
-       * resident per SM, parallel half-empty warps beat one full warp */
+      /* slot -> thread map: the staged chains are dealt round-robin to the warps (with few warps resident
+       * per SM, parallel part-filled warps beat one full warp) */
+#ifndef SLGPU_SLOTMAP_CONTIGUOUS /* measured: the strided map is ~14% faster on config #3 despite 4-way bank conflicts */
       const int slot = (tid & 31) * (NT / 32) + (tid >> 5);
-      if (slot < nacc) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
+      const bool mine = slot < nacc;
+#else
+      const int per = (nacc + NT / 32 - 1) / (NT / 32);
+      const int slot = (tid >> 5) * per + (tid & 31);
+      const bool mine = (tid & 31) < per && slot < nacc;
+#endif
+      if (mine) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
         s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
                                                        s_cnt[slot], p.prop_norm);
       }
