@@ -1,5 +1,7 @@
 """In-tree nvcc build of the engine (libslgpu.so) and the built-in likelihood plugin
 (libslgpu_targets.so) for sm_100a.  The .so files are git-ignored but travel to the GPU box."""
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -24,11 +26,36 @@ def nvcc():
     return exe
 
 
-def _stale(out, deps):
-    if not os.path.exists(out):
+def _digest(deps, flags):
+    """Content hash of the sources and flags: file times do not survive the copy to the GPU box."""
+    h = hashlib.sha256(" ".join(flags).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(out, digest):
+    try:
+        return not os.path.exists(out) or open(out + ".srchash").read().strip() != digest
+    except OSError:
         return True
-    t = os.path.getmtime(out)
-    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(cmd, out, digest, verbose):
+    """Build under an exclusive lock (ranks of one node may race here) and record the source hash."""
+    with open(out + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if _stale(out, digest):
+            tmp = out + ".tmp.%d" % os.getpid()
+            full = [c if c != out else tmp for c in cmd]
+            if verbose:
+                print(" ".join(full))
+            subprocess.check_call(full)
+            os.replace(tmp, out)
+            with open(out + ".srchash", "w") as f:
+                f.write(digest)
 
 
 def _headers():
@@ -39,21 +66,23 @@ def _headers():
 
 def build_engine(force=False, verbose=False):
     src = os.path.join(CSRC, "engine.cu")
-    if force or _stale(ENGINE_SO, [src] + _headers()):
-        cmd = [nvcc()] + ARCH + COMMON + ["-O2", "-o", ENGINE_SO, src, "-ldl"]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
+    flags = ARCH + COMMON + ["-O2", "-ldl"]
+    digest = _digest([src] + _headers(), flags)
+    if force and os.path.exists(ENGINE_SO + ".srchash"):
+        os.remove(ENGINE_SO + ".srchash")
+    if _stale(ENGINE_SO, digest):
+        _compile([nvcc()] + ARCH + COMMON + ["-O2", "-o", ENGINE_SO, src, "-ldl"], ENGINE_SO, digest, verbose)
     return ENGINE_SO
 
 
 def build_plugin(src, out, force=False, verbose=False, extra=()):
     """Compile a likelihood plugin translation unit (it includes slgpu_device.cuh) into a .so."""
-    if force or _stale(out, [src] + _headers()):
-        cmd = [nvcc()] + ARCH + COMMON + ["-O3", "-o", out, src] + list(extra)
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
+    flags = ARCH + COMMON + ["-O3"] + list(extra)
+    digest = _digest([src] + _headers(), flags)
+    if force and os.path.exists(out + ".srchash"):
+        os.remove(out + ".srchash")
+    if _stale(out, digest):
+        _compile([nvcc()] + ARCH + COMMON + ["-O3", "-o", out, src] + list(extra), out, digest, verbose)
     return out
 
 

@@ -834,7 +834,7 @@ slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double
   if (st != SLGPU_OK) return st;
   if (chain >= e->C) return fail(SLGPU_E_ARG, "chain out of range");
   if ((st = sync_all(e)) != SLGPU_OK) return st;
-  const size_t C = e->C, d = e->cfg.nDims, nL = d * (d + 1) / 2;
+  const size_t d = e->cfg.nDims, nL = d * (d + 1) / 2;
   std::vector<double> packed(nL);
   const double* lsrc = e->P.L + (size_t)(chain / SLGPU_L_TILE) * nL * SLGPU_L_TILE + chain % SLGPU_L_TILE;
   CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), lsrc, SLGPU_L_TILE * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
