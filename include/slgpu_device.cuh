@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
 }  // namespace slgpu
 
 #include "slgpu_step_fast.cuh"
+#include "slgpu_step_pair.cuh"
 
 namespace slgpu {
 
@@ -551,13 +552,19 @@ inline unsigned grid_for(const slgpu_step_params* p, unsigned threads = SLGPU_TH
   return (p->n_stacks + per_block - 1) / per_block;
 }
 
-/* development switch: SLGPU_STEP_VARIANT=generic forces the runtime-d kernel */
+#ifndef SLGPU_DEFAULT_PAIR
+#define SLGPU_DEFAULT_PAIR 0
+#endif
+
+/* development switch: SLGPU_STEP_VARIANT = generic | single | pair picks the step kernel */
 inline int step_variant() {
   const char* v = getenv("SLGPU_STEP_VARIANT");
   if (!v) return 0;
   if (!strcmp(v, "smem")) return 1;
   if (!strcmp(v, "global")) return 2;
   if (!strcmp(v, "generic")) return 3;
+  if (!strcmp(v, "pair")) return 4;
+  if (!strcmp(v, "single")) return 5;
   return 0;
 }
 
@@ -575,7 +582,18 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
     return (int)cudaGetLastError();
   }
   if constexpr (D > 0 && D <= 32) {
-    if (step_variant() != 3) {
+    const int variant = step_variant();
+    if ((variant == 4 || (variant == 0 && SLGPU_DEFAULT_PAIR)) && p->n_temps <= 16) { /* two lanes per chain */
+      constexpr int NT = SLGPU_PAIR_THREADS;
+      auto kern = pt_step_pair_kernel<Lik, D, NT>;
+      const size_t smem = pair_smem_bytes<D, NT>(p->n_temps);
+      static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes<D, NT>(1));
+      if (attr != cudaSuccess) return (int)attr;
+      const unsigned spw = 16u / p->n_temps, per_block = spw * (NT / 32);
+      kern<<<(p->n_stacks + per_block - 1) / per_block, NT, smem, (cudaStream_t)stream>>>(*p);
+      return (int)cudaGetLastError();
+    }
+    if (variant != 3) {
       constexpr int NT = SLGPU_FAST_THREADS;
       auto kern = pt_step_fast_kernel<Lik, D, NT>;
       const size_t smem = fast_smem_bytes<D, NT>(p->n_temps);

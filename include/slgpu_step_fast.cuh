@@ -43,6 +43,9 @@ __device__ __forceinline__ double div_by(double n, double c, double rc) {
 #ifndef SLGPU_NORMALS_UNROLL
 #define SLGPU_NORMALS_UNROLL 1
 #endif
+#ifndef SLGPU_LDL
+#define SLGPU_LDL(p) (*(p)) /* load of an L entry; development knob: __ldcg / __ldcs / __ldca */
+#endif
 #ifndef SLGPU_COLBLOCK
 #define SLGPU_COLBLOCK 2
 #endif
@@ -76,10 +79,10 @@ __device__ __forceinline__ void gemv_block(const double* Lc, const double* zs, i
     const double* Lk = Lc + k * kLs;
     double col0[D], col1[D];
 #pragma unroll
-    for (int j = K0; j < D; ++j) col0[j] = Lk[(j * (j + 1) / 2) * kLs];
+    for (int j = K0; j < D; ++j) col0[j] = SLGPU_LDL(Lk + (j * (j + 1) / 2) * kLs);
     if (two) {
 #pragma unroll
-      for (int j = K0; j < D; ++j) col1[j] = Lk[(j * (j + 1) / 2 + 1) * kLs];
+      for (int j = K0; j < D; ++j) col1[j] = SLGPU_LDL(Lk + (j * (j + 1) / 2 + 1) * kLs);
     }
     gemv_col<D, K0, K1>(k, col0, zs[k * zstride], s_n0[k], nscale, fresh, a);
     if (two) gemv_col<D, K0, K1>(k + 1, col1, zs[(k + 1) * zstride], s_n0[k + 1], nscale, fresh, a);
@@ -129,10 +132,10 @@ __device__ __forceinline__ void shaper_block(double* Lc, double scale, double* x
     double* Lk = Lc + k * kLs; /* column k: L(j,k) = Lk[(j(j+1)/2)*ls] */
     double col0[D], col1[D];
 #pragma unroll
-    for (int j = K0; j < D; ++j) col0[j] = Lk[(j * (j + 1) / 2) * kLs];
+    for (int j = K0; j < D; ++j) col0[j] = SLGPU_LDL(Lk + (j * (j + 1) / 2) * kLs);
     if (two) {
 #pragma unroll
-      for (int j = K0; j < D; ++j) col1[j] = Lk[(j * (j + 1) / 2 + 1) * kLs];
+      for (int j = K0; j < D; ++j) col1[j] = SLGPU_LDL(Lk + (j * (j + 1) / 2 + 1) * kLs);
     }
     shaper_col<D, K0, K1>(k, Lk, col0, scale, xs, xst, fr, fst);
     if (two) shaper_col<D, K0, K1>(k + 1, Lk + kLs, col1, scale, xs, xst, fr, fst);
