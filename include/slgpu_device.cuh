@@ -84,7 +84,7 @@ __device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b 
 __device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }
 
 /* bouncyBounds, one coordinate -- src/infer/sampler.cpp:23-56 */
-__device__ __forceinline__ double bounce1(double v, double mn, double mx) {
+__device__ __noinline__ double bounce1_reflect(double v, double mn, double mx) {
   const double delta = mx - mn;
   double result = v;
   if (v > mx) {
@@ -100,6 +100,11 @@ __device__ __forceinline__ double bounce1(double v, double mn, double mx) {
     result = (nSteps % 2 == 0) ? mn + stillToGo : mx - stillToGo;
   }
   return result;
+}
+/* in-bounds values (the common case) cost two compares; the reflection arithmetic is out of line */
+__device__ __forceinline__ double bounce1(double v, double mn, double mx) {
+  if (v > mx || v < mn) return bounce1_reflect(v, mn, mx);
+  return v;
 }
 
 /* RegressionAdapter::predict -- src/infer/adaptive.cpp:94-106 */
@@ -532,6 +537,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
 
 #include "slgpu_step_fast.cuh"
 #include "slgpu_step_pair.cuh"
+#include "slgpu_step_quad.cuh"
 
 namespace slgpu {
 
@@ -555,6 +561,9 @@ inline unsigned grid_for(const slgpu_step_params* p, unsigned threads = SLGPU_TH
 #ifndef SLGPU_DEFAULT_PAIR
 #define SLGPU_DEFAULT_PAIR 0
 #endif
+#ifndef SLGPU_DEFAULT_QUAD
+#define SLGPU_DEFAULT_QUAD 0
+#endif
 
 /* development switch: SLGPU_STEP_VARIANT = generic | single | pair picks the step kernel */
 inline int step_variant() {
@@ -565,6 +574,7 @@ inline int step_variant() {
   if (!strcmp(v, "generic")) return 3;
   if (!strcmp(v, "pair")) return 4;
   if (!strcmp(v, "single")) return 5;
+  if (!strcmp(v, "quad")) return 6;
   return 0;
 }
 
@@ -583,6 +593,22 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
   }
   if constexpr (D > 0 && D <= 32) {
     const int variant = step_variant();
+    if ((variant == 6 || (variant == 0 && SLGPU_DEFAULT_QUAD)) && p->n_temps <= 8) { /* L in shared memory, four lanes per chain */
+      constexpr int NT = SLGPU_QUAD_THREADS;
+      auto kern = pt_step_quad_kernel<Lik, D, NT>;
+      const size_t smem = quad_smem_bytes<D, NT>(p->n_temps, p->n_job_types);
+      if (smem <= 200 * 1024) {
+        static size_t attr_set = 0;
+        if (smem > attr_set) {
+          const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (attr != cudaSuccess) return (int)attr;
+          attr_set = smem;
+        }
+        const unsigned spw = 8u / p->n_temps, per_block = spw * (NT / 32);
+        kern<<<(p->n_stacks + per_block - 1) / per_block, NT, smem, (cudaStream_t)stream>>>(*p);
+        return (int)cudaGetLastError();
+      }
+    }
     if ((variant == 4 || (variant == 0 && SLGPU_DEFAULT_PAIR)) && p->n_temps <= 16) { /* two lanes per chain */
       constexpr int NT = SLGPU_PAIR_THREADS;
       auto kern = pt_step_pair_kernel<Lik, D, NT>;

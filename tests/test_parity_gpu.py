@@ -91,18 +91,20 @@ def test_philox_bit_exact(name, rounds):
         _compare(eng, orc, w, "philox %d rounds" % rounds)
 
 
-def test_generic_kernel_matches_fast_kernel(monkeypatch):
-    """The runtime-d kernel and the specialised D=20 kernel are the same function."""
+def test_step_kernel_variants_agree(monkeypatch):
+    """The runtime-d kernel, the thread-per-chain kernel, the lane-pair kernel and the shared-memory
+    lane-quad kernel are the same function: bit-identical state, rows and factors."""
     w = configs.workload("config3", S=12)
     res = []
-    for variant in ("generic", ""):
+    for variant in ("generic", "single", "pair", "quad"):
         monkeypatch.setenv("SLGPU_STEP_VARIANT", variant)
         with engine_for(w, seed=3) as eng:
             eng.init_chains()
             eng.step_rounds(59)
             res.append((eng.last_rows(), eng.drain(), eng.shaper(5)[0]))
-    for a, b in zip(*res):
-        assert np.array_equal(a, b)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a, b)
 
 
 def test_golden_fixture():
