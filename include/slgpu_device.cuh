@@ -203,6 +203,13 @@ __device__ __forceinline__ double* l_base(double* L, u32 c, u32 nL) {
   return L + (size_t)(c / SLGPU_L_TILE) * nL * SLGPU_L_TILE + (c % SLGPU_L_TILE);
 }
 
+/* entry (r,k), k <= r, of chain c's factor in whichever layout the dimension uses */
+__device__ __forceinline__ double& l_elem(double* L, u32 c, int d, int r, int k) {
+  const size_t nL = (size_t)d * (d + 1) / 2;
+  if (SLGPU_L_LAYOUT((u32)d) == SLGPU_L_COLMAJOR) return L[(size_t)c * nL + (size_t)k * d - (size_t)k * (k - 1) / 2 + (size_t)(r - k)];
+  return l_base(L, c, (u32)nL)[(size_t)(r * (r + 1) / 2 + k) * SLGPU_L_TILE];
+}
+
 /* regression statistics: P[(k*T + t)*S + s], k < 9 -- coalesced over the stacks of a tier for the reduce */
 __device__ __forceinline__ size_t pidx(const slgpu_step_params& p, int k, int t, u32 s) {
   return ((size_t)k * p.n_temps + (size_t)t) * p.n_stacks + s;
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
     p.x[(size_t)i * C + c] = x[i];
   for (int r = 0; r < d; ++r)
     for (int k = 0; k <= r; ++k)
-      l_base(p.L, c, (u32)(d * (d + 1) / 2))[(size_t)(r * (r + 1) / 2 + k) * SLGPU_L_TILE] = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
+      l_elem(p.L, c, d, r, k) = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
   const double b = p.ladder[m.t];
   p.energy[c] = e;
   p.row_sigma[c] = 1.0;
@@ -538,6 +545,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
 #include "slgpu_step_fast.cuh"
 #include "slgpu_step_pair.cuh"
 #include "slgpu_step_quad.cuh"
+#include "slgpu_step_warp.cuh"
 
 namespace slgpu {
 
@@ -586,6 +594,32 @@ int launch_init_t(const slgpu_step_params* p, void* stream) {
 }
 template <class Lik, int D>
 int launch_step_t(const slgpu_step_params* p, void* stream) {
+  if (SLGPU_L_LAYOUT(p->n_dims) == SLGPU_L_COLMAJOR) { /* d > 32: one warp per chain, whole stacks per block */
+    const unsigned spb = warp_stacks_per_block(p->n_temps), warps = spb * p->n_temps;
+    const size_t smem = warp_smem_bytes(p, warps);
+    const unsigned grid = (p->n_stacks + spb - 1) / spb, threads = warps * 32;
+    const int rm = (int)(p->n_dims + 31) / 32;
+#define SLGPU_WARP_LAUNCH(RMV, MAXTV)                                                                                     \
+  {                                                                                                                       \
+    auto kern = pt_step_warp_kernel<Lik, RMV, MAXTV>;                                                                     \
+    static size_t attr_set = 48 * 1024;                                                                                   \
+    if (smem > attr_set) {                                                                                                \
+      const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      if (attr != cudaSuccess) return (int)attr;                                                                          \
+      attr_set = smem;                                                                                                    \
+    }                                                                                                                     \
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*p);                                                              \
+  }
+    if (threads <= 256) {
+      if (rm <= 2) SLGPU_WARP_LAUNCH(2, 256) else if (rm == 3) SLGPU_WARP_LAUNCH(3, 256) else SLGPU_WARP_LAUNCH(4, 256)
+    } else if (threads <= 512) {
+      if (rm <= 2) SLGPU_WARP_LAUNCH(2, 512) else if (rm == 3) SLGPU_WARP_LAUNCH(3, 512) else SLGPU_WARP_LAUNCH(4, 512)
+    } else {
+      if (rm <= 2) SLGPU_WARP_LAUNCH(2, 1024) else if (rm == 3) SLGPU_WARP_LAUNCH(3, 1024) else SLGPU_WARP_LAUNCH(4, 1024)
+    }
+#undef SLGPU_WARP_LAUNCH
+    return (int)cudaGetLastError();
+  }
   constexpr int JS = StaticJobs<Lik, D>::value;
   if (JS > 0 && p->n_job_types != (uint32_t)JS) {
     pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);

@@ -26,6 +26,11 @@ extern "C" {
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
 #define SLGPU_L_TILE 128u   /* chains per tile of the packed-L store (see slgpu_step_params.L) */
+/* how the packed L factors are stored (slgpu_step_params.L): small dimensions are tiled by 128 chains for the
+ * thread-per-chain kernels; large ones are kept per chain, packed column-major, for the warp-per-chain kernel */
+#define SLGPU_L_TILED 0
+#define SLGPU_L_COLMAJOR 1
+#define SLGPU_L_LAYOUT(n_dims) ((n_dims) > 32u ? SLGPU_L_COLMAJOR : SLGPU_L_TILED)
 #define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
 
 enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
@@ -55,7 +60,9 @@ typedef struct slgpu_step_params {
   const double* initial;   /* [d] or NULL (useInitial) */
   /* chain state */
   double* x;               /* [d][C]  sample of the last row */
-  double* L;               /* [ceil(C/128)][d(d+1)/2][128]  ProposalShaper L_ (adaptive.cpp:158) */
+  double* L;               /* ProposalShaper L_ (adaptive.cpp:158), lower triangle.  d <= 32 (SLGPU_L_TILED):
+                            * [ceil(C/128)][d(d+1)/2][128], row-major packed.  d > 32 (SLGPU_L_COLMAJOR):
+                            * [C][d(d+1)/2], column-major packed: L(j,k) at k*d - k(k-1)/2 + (j-k) */
   double* energy;          /* [C] */
   double* row_sigma;       /* [C] sigma stored in the last row (stale after a reject, chainarray.cpp:102-106) */
   double* row_beta;        /* [C] */

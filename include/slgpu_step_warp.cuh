@@ -1,0 +1,369 @@
+/*
+ * slgpu_step_warp.cuh -- pt_step for large dimensions (32 < d <= 128): ONE WARP PER CHAIN
+ * (included by slgpu_device.cuh).
+ *
+ * At d = 100 a chain's factor is 40 KB and a stack of 8 is 323 KB: nothing fits on chip, and a config such as
+ * BASELINE #4 (1024 stacks x 8) has only 8192 chains -- too few threads for a thread-per-chain kernel.  So
+ * the O(d^2) work of one chain is spread over the 32 lanes of a warp and the factors are streamed from HBM:
+ *   - lane l owns rows j = l + 32m (m < 4) of x, of the proposal accumulator, of the jump and of L;
+ *   - L is stored per chain, packed COLUMN-major (slgpu_l_layout): column k, rows k..d-1, is contiguous, so a
+ *     column sweep (proposal GEMV and rank-1 update both walk columns) is one coalesced warp access per row group;
+ *   - a row still accumulates k ascending with the diagonal last, the Frobenius norm uses the canonical
+ *     32-slot order (slot l = rows l, l+32, ...; halving tree = __shfl_down), so results equal the oracle's bit for bit;
+ *   - accept / reject is warp-uniform: the shaper update runs in place without divergence;
+ *   - the chain's scalars are replicated over the lanes; normals, proposal and the running jump go through a
+ *     per-warp vector in shared memory; the functor evaluates job types lane, lane+32, ... and every lane adds
+ *     the J values in job order;
+ *   - a block holds whole stacks (T warps each); the swap sweep of a stack goes through shared memory.
+ */
+#ifndef SLGPU_STEP_WARP_CUH
+#define SLGPU_STEP_WARP_CUH
+
+namespace slgpu {
+
+/* row groups per lane: RM = ceil(d / 32) is a template parameter (2, 3 or 4) so that small d carries no dead rows */
+#ifndef SLGPU_WARP_REGS
+#define SLGPU_WARP_REGS 32 /* register budget per thread: 65536 / budget threads resident per SM */
+#endif
+#define SLGPU_WARP_MINBLOCKS(maxt) (65536 / ((maxt) * SLGPU_WARP_REGS))
+#ifndef SLGPU_WARP_GEMV_UNROLL
+#define SLGPU_WARP_GEMV_UNROLL 4
+#endif
+constexpr int kWarpGemvUnroll = SLGPU_WARP_GEMV_UNROLL;
+
+/* dynamic shared memory: per warp a vector [d+1] and [J] job values; per stack the swap scratch */
+inline size_t warp_smem_bytes(const slgpu_step_params* p, unsigned warps) {
+  const size_t d = p->n_dims, J = p->n_job_types, T = p->n_temps, stacks = warps / T;
+  return (warps * (d + 1) + warps * J + stacks * (3 * T + T * d)) * sizeof(double) + stacks * T * sizeof(int);
+}
+
+/* stacks per block: as many whole stacks as fit 8 warps (at least one) */
+inline unsigned warp_stacks_per_block(unsigned n_temps) { return n_temps >= 8 ? 1u : 8u / n_temps; }
+
+template <class Lik, int RM, int MAXT>
+__global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp_kernel(const slgpu_step_params p) {
+  const int T = (int)p.n_temps, d = (int)p.n_dims, J = (int)p.n_job_types;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5, spb = nwarps / T;
+  const int sl = warp / T, t = warp - sl * T;
+  const u32 s = blockIdx.x * (u32)spb + (u32)sl;
+  const bool active = s < p.n_stacks; /* warp-uniform */
+  const size_t C = (size_t)p.n_stacks * p.n_temps;
+  const u32 c = active ? s * (u32)T + (u32)t : 0u;
+  const u32 gchain = p.stack_offset * p.n_temps + c;
+  const bool replay = (p.rng_mode == SLGPU_RNG_REPLAY);
+  const size_t nL = (size_t)d * (d + 1) / 2;
+
+  extern __shared__ double s_dyn[];
+  double* const vec = s_dyn + (size_t)warp * (d + 1);                       /* z, then x', then the running jump */
+  double* const fv = s_dyn + (size_t)nwarps * (d + 1) + (size_t)warp * J;   /* per-job values */
+  double* const sw = s_dyn + (size_t)nwarps * (d + 1) + (size_t)nwarps * J + (size_t)sl * (3 * T + T * d);
+  double* const sw_e = sw;           /* [T] energies */
+  double* const sw_b = sw + T;       /* [T] betas */
+  double* const sw_u = sw + 2 * T;   /* [T] swap uniforms */
+  double* const sw_x = sw + 3 * T;   /* [T][d] samples */
+  int* const sw_acc = (int*)(s_dyn + (size_t)nwarps * (d + 1) + (size_t)nwarps * J + (size_t)spb * (3 * T + T * d)) + sl * T;
+  __shared__ double s_mn[SLGPU_MAX_DIMS], s_mx[SLGPU_MAX_DIMS], s_n0[SLGPU_MAX_DIMS];
+  __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
+  for (int i = tid; i < d; i += blockDim.x) {
+    s_mn[i] = p.mn[i];
+    s_mx[i] = p.mx[i];
+    s_n0[i] = p.n0_diag[i];
+  }
+  for (int i = tid; i < T; i += blockDim.x) {
+    s_w[3 * i + 0] = p.sig_w[3 * i + 0];
+    s_w[3 * i + 1] = p.sig_w[3 * i + 1];
+    s_w[3 * i + 2] = p.sig_w[3 * i + 2];
+    s_lad[i] = p.ladder[i];
+  }
+  __syncthreads();
+
+  const Lik lik(p.payload);
+  double* const Lg = p.L + (size_t)c * nL; /* column k starts at ck = k*d - k(k-1)/2; L(j,k) = Lg[ck + j - k] */
+  double x[RM];
+#pragma unroll
+  for (int m = 0; m < RM; ++m) {
+    const int j = lane + 32 * m;
+    x[m] = (j < d) ? p.x[(size_t)j * C + c] : 0.0;
+  }
+  double Ps[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Ps[k] = active ? p.p_sig[pidx(p, k, t, s)] : 0.0;
+  double energy = p.energy[c], row_sigma = p.row_sigma[c], row_beta = p.row_beta[c];
+  double sigma = p.sigma[c], beta = p.beta[c], nscale = p.nscale[c], sh_count = p.sh_count[c];
+  int accepted = p.accepted[c], swap_type = p.swap_type[c];
+  u32 lg_accepts = p.lg_accepts[c], lg_swaps = p.lg_swaps[c], lg_att = p.lg_swap_attempts[c];
+  double lg_min_e = p.lg_min_energy[c];
+  const double w3[3] = {s_w[3 * t], s_w[3 * t + 1], s_w[3 * t + 2]};
+  const int W = (int)p.swap_interval;
+
+  for (u32 it = 0; it < p.n_rounds; ++it) {
+    const u64 r = p.round_begin + it;
+    bool acc = false;
+    if (active) {
+      /* ---- normals: lane l makes the Box-Muller pairs l, l+32, ... ---- */
+      const double* zr = replay ? p.rp_z + ((size_t)r * C + c) * d : nullptr;
+      for (int kp = lane; kp < (d + 1) / 2; kp += 32) {
+        double z0, z1 = 0.0;
+        if (replay) {
+          z0 = zr[2 * kp];
+          if (2 * kp + 1 < d) z1 = zr[2 * kp + 1];
+        } else {
+          double ua, ub, sn, cs;
+          philox_draw(p.seed, gchain, r, 0, (u32)kp, ua, ub);
+          const double Rr = sqrt(-2.0 * slm_log(ua));
+          slm_sincos2pi(ub, &sn, &cs);
+          z0 = Rr * cs;
+          z1 = Rr * sn;
+        }
+        vec[2 * kp] = z0;
+        if (2 * kp + 1 < d) vec[2 * kp + 1] = z1;
+      }
+      __syncwarp();
+      /* ---- proposal: a_j = sum_{k<=j} fma(N_jk, z_k, .), k ascending; one coalesced column segment per row group ---- */
+      const bool fresh = (sh_count == p.sh_count0);
+      double a[RM];
+#pragma unroll
+      for (int m = 0; m < RM; ++m) a[m] = 0.0;
+      {
+        size_t ck = 0;
+#pragma unroll kWarpGemvUnroll
+        for (int k = 0; k < d; ++k) {
+          const double zk = vec[k];
+          const double n0k = s_n0[k];
+#pragma unroll
+          for (int m = 0; m < RM; ++m) {
+            const int j = lane + 32 * m;
+            if (32 * m + 31 >= k && j >= k && j < d) {
+              double njk = Lg[ck + (size_t)(j - k)] * nscale;
+              if (j == k) njk = fresh ? n0k : njk + 1e-4;
+              a[m] = fma(njk, zk, a[m]);
+            }
+          }
+          ck += (size_t)(d - k);
+        }
+      }
+      __syncwarp(); /* z fully consumed: the vector takes the proposal */
+#pragma unroll
+      for (int m = 0; m < RM; ++m) {
+        const int j = lane + 32 * m;
+        if (j < d) {
+          a[m] = bounce1(x[m] + a[m] * sigma, s_mn[j], s_mx[j]);
+          vec[j] = a[m];
+        }
+      }
+      __syncwarp();
+      /* ---- energy: job types lane, lane+32, ...; every lane adds the J values in job order ---- */
+      for (int jj = lane; jj < J; jj += 32) fv[jj] = lik((u32)jj, vec, (u32)d);
+      __syncwarp();
+      double e_new = 0.0;
+      for (int jj = 0; jj < J; ++jj) e_new += fv[jj];
+      /* ---- acceptProposal (chainarray.cpp:30-45), append (:94-121) ---- */
+      if (!isinf(e_new)) {
+        double u;
+        if (replay) u = p.rp_umh[(size_t)r * C + c];
+        else { double ub; philox_draw(p.seed, gchain, r, 1, 0, u, ub); }
+        const double deltaEnergy = e_new - energy;
+        acc = u < slm_exp(-1.0 * beta * deltaEnergy);
+      }
+      double xs[RM]; /* the accepted jump, then the running rank-1 vector */
+      if (acc) {
+#pragma unroll
+        for (int m = 0; m < RM; ++m) {
+          xs[m] = a[m] - x[m];
+          if (lane + 32 * m < d) x[m] = a[m];
+        }
+        energy = e_new;
+        row_sigma = sigma;
+        row_beta = beta;
+      }
+      accepted = acc ? 1 : 0;
+      swap_type = 0;
+      const double logtemper = -slm_log(row_beta);
+      stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
+      sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
+      /* ---- ProposalShaper::update (adaptive.cpp:173-209), in place: accept is warp-uniform ---- */
+      if (acc) {
+        const double eps = 1e-18;
+        sh_count += 1.0;
+        const double sq = sqrt(sh_count);
+        const double rsq = 1.0 / sq;
+        const double scale = sqrt((sh_count - 1.0) / sh_count);
+        double fr[RM];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < RM; ++m) {
+          const int j = lane + 32 * m;
+          xs[m] = div_by(xs[m], sq, rsq);
+          fr[m] = 0.0;
+          if (j < d) vec[j] = xs[m];
+        }
+        __syncwarp();
+        size_t ck = 0;
+        for (int k = 0; k < d; ++k) {
+          const double xk = vec[k];
+          const double Lkk = Lg[ck] * scale;
+          const double V = smax(eps, Lkk);
+          const double rV = 1.0 / V;
+          const double rr = sqrt(V * V + xk * xk);
+          const double cc = div_by(rr, V, rV);
+          const double ss = div_by(xk, V, rV);
+          const double rc = 1.0 / cc;
+          __syncwarp();
+#pragma unroll
+          for (int m = 0; m < RM; ++m) {
+            const int j = lane + 32 * m;
+            if (32 * m + 31 >= k && j < d) {
+              if (j == k) {
+                Lg[ck] = rr;
+                fr[m] = fma(rr, rr, fr[m]); /* the diagonal closes row k's sum */
+              } else if (j > k) {
+                const size_t o = ck + (size_t)(j - k);
+                double Ljk = Lg[o] * scale;
+                Ljk = div_by(Ljk + ss * xs[m], cc, rc);
+                Lg[o] = Ljk;
+                xs[m] = cc * xs[m] - ss * Ljk;
+                fr[m] = fma(Ljk, Ljk, fr[m]);
+                if (j == k + 1) vec[j] = xs[m]; /* the next column's head needs it */
+              }
+            }
+          }
+          __syncwarp();
+          ck += (size_t)(d - k);
+        }
+        /* |L|_F: slot l = rows l, l+32, ... in order; halving tree over the 32 slots */
+        double slot = 0.0;
+#pragma unroll
+        for (int m = 0; m < RM; ++m)
+          if (lane + 32 * m < d) slot += fr[m];
+#pragma unroll
+        for (int mm = 16; mm > 0; mm >>= 1) {
+          const double other = __shfl_down_sync(0xffffffffu, slot, mm);
+          if (lane < mm) slot += other;
+        }
+        const double frob = sqrt(__shfl_sync(0xffffffffu, slot, 0));
+        nscale = p.prop_norm / smax(frob, eps);
+      }
+    }
+
+    /* ================= swap sweep of the stack, through shared memory ================= */
+    double mid_e = energy;
+    int mid_acc = accepted;
+    const bool swapRound = (T > 1) && ((r + 2) % (u64)W == 0); /* block-uniform */
+    if (swapRound) {
+      if (lane == 0) {
+        double u_sw = 0.0;
+        if (active && t < T - 1) {
+          if (replay) u_sw = p.rp_uswap[(size_t)r * C + c];
+          else { double ub; philox_draw(p.seed, gchain, r, 2, 0, u_sw, ub); }
+        }
+        sw_e[t] = energy;
+        sw_b[t] = beta;
+        sw_u[t] = u_sw;
+        sw_acc[t] = accepted;
+      }
+#pragma unroll
+      for (int m = 0; m < RM; ++m) {
+        const int j = lane + 32 * m;
+        if (j < d) sw_x[(size_t)t * d + j] = x[m];
+      }
+      __syncthreads();
+      int cur = T - 1, my_src = t, mid_src = t;
+      bool my_swapped = false;
+      for (int tt = T - 2; tt >= 0; --tt) {
+        const double deltaEnergy = sw_e[tt] - sw_e[cur];
+        const double deltaBeta = sw_b[tt] - sw_b[tt + 1];
+        const bool swp = sw_u[tt] < slm_exp(deltaEnergy * deltaBeta);
+        if (t == tt + 1) my_src = swp ? tt : cur;
+        if (t == tt) { my_swapped = swp; mid_src = swp ? cur : tt; }
+        if (!swp) cur = tt;
+      }
+      if (t == 0) my_src = cur;
+      const double lb = slm_log(beta);
+      const double lbh = (t + 1 < T) ? slm_log(sw_b[t + 1]) : lb;
+      mid_e = sw_e[mid_src];
+      mid_acc = sw_acc[mid_src];
+      energy = sw_e[my_src];
+      accepted = sw_acc[my_src];
+#pragma unroll
+      for (int m = 0; m < RM; ++m) {
+        const int j = lane + 32 * m;
+        if (j < d) x[m] = sw_x[(size_t)my_src * d + j];
+      }
+      if (active && t < T - 1) {
+        swap_type = my_swapped ? 1 : 2;
+        if (lane == 0) {
+          double Pb[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Pb[k] = p.p_beta[pidx(p, k, t, s)];
+          stats_accumulate<1>(Pb, 0.0, 4.0, lb - lbh, lb, my_swapped);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) p.p_beta[pidx(p, k, t, s)] = Pb[k];
+        }
+      }
+      if (t > 0) beta = s_lad[t];
+      __syncthreads(); /* the scratch is reused next swap round */
+    }
+
+    if (active) {
+      lg_min_e = smin(lg_min_e, mid_e);
+      lg_accepts += (u32)mid_acc;
+      lg_swaps += (swap_type == 1);
+      lg_att += (swap_type != 0);
+      if (t == 0) {
+        const double nn = (double)(r + 1);
+        const double rnn = 1.0 / nn;
+        double* row = p.rows_out ? p.rows_out + ((size_t)it * p.n_stacks + s) * (d + SLGPU_ROW_EXTRA) : nullptr;
+#pragma unroll
+        for (int m = 0; m < RM; ++m) {
+          const int j = lane + 32 * m;
+          if (j < d) {
+            const size_t o = (size_t)j * p.n_stacks + s;
+            const double mo = p.ep_m[o];
+            const double xi = x[m];
+            const double newM = mo + div_by(xi - mo, nn, rnn);
+            p.ep_s[o] = p.ep_s[o] + (xi - mo) * (xi - newM);
+            p.ep_m[o] = newM;
+            if (row) row[j] = xi;
+          }
+        }
+        if (row && lane == 0) {
+          row[d] = energy;
+          row[d + 1] = row_sigma;
+          row[d + 2] = row_beta;
+          row[d + 3] = (double)accepted;
+          row[d + 4] = (double)swap_type;
+        }
+      }
+    }
+  }
+
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < RM; ++m) {
+      const int j = lane + 32 * m;
+      if (j < d) p.x[(size_t)j * C + c] = x[m];
+    }
+    if (lane == 0) {
+      p.energy[c] = energy;
+      p.row_sigma[c] = row_sigma;
+      p.row_beta[c] = row_beta;
+      p.sigma[c] = sigma;
+      p.beta[c] = beta;
+      p.nscale[c] = nscale;
+      p.sh_count[c] = sh_count;
+      p.accepted[c] = accepted;
+      p.swap_type[c] = swap_type;
+      p.lg_accepts[c] = lg_accepts;
+      p.lg_swaps[c] = lg_swaps;
+      p.lg_swap_attempts[c] = lg_att;
+      p.lg_min_energy[c] = lg_min_e;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) p.p_sig[pidx(p, k, t, s)] = Ps[k];
+    }
+  }
+}
+
+}  // namespace slgpu
+
+#endif

@@ -836,8 +836,15 @@ slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double
   if ((st = sync_all(e)) != SLGPU_OK) return st;
   const size_t d = e->cfg.nDims, nL = d * (d + 1) / 2;
   std::vector<double> packed(nL);
-  const double* lsrc = e->P.L + (size_t)(chain / SLGPU_L_TILE) * nL * SLGPU_L_TILE + chain % SLGPU_L_TILE;
-  CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), lsrc, SLGPU_L_TILE * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
+  if (SLGPU_L_LAYOUT((uint32_t)d) == SLGPU_L_COLMAJOR) {
+    std::vector<double> colp(nL);
+    CU_TRY(cudaMemcpy(colp.data(), e->P.L + (size_t)chain * nL, nL * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < d; ++k)
+      for (size_t j = k; j < d; ++j) packed[j * (j + 1) / 2 + k] = colp[k * d - k * (k - 1) / 2 + (j - k)];
+  } else {
+    const double* lsrc = e->P.L + (size_t)(chain / SLGPU_L_TILE) * nL * SLGPU_L_TILE + chain % SLGPU_L_TILE;
+    CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), lsrc, SLGPU_L_TILE * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
+  }
   double cnt = 0.0, ns = 0.0;
   CU_TRY(cudaMemcpy(&cnt, e->P.sh_count + chain, sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(&ns, e->P.nscale + chain, sizeof(double), cudaMemcpyDeviceToHost));
