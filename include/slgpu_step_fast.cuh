@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       const int nacc = s_nacc[par];
       /* slot -> thread map: the staged chains are dealt round-robin to the warps (with few warps resident
        * per SM, parallel part-filled warps beat one full warp) */
-#ifndef SLGPU_SLOTMAP_CONTIGUOUS /* measured: the strided map is ~14% faster on config #3 despite 4-way bank conflicts */
+#if !defined(SLGPU_SLOTMAP_STRIDED) && !defined(SLGPU_SLOTMAP_CONTIGUOUS) /* measured on config #3: dense 74, strided 78, contiguous runs 95 us per round */
+      const int slot = tid; /* fill the first warps completely */
+      const bool mine = slot < nacc;
+#elif defined(SLGPU_SLOTMAP_STRIDED)
       const int slot = (tid & 31) * (NT / 32) + (tid >> 5);
       const bool mine = slot < nacc;
 #else
