@@ -22,15 +22,6 @@
 
 namespace slgpu {
 
-/* n / c given rc = RN(1/c): q0 = RN(n rc), r = n - q0 c (exact, fma), q = RN(q0 + r rc).  By Markstein's
- * theorem this is the correctly rounded quotient -- the same bits as the IEEE division the reference
- * and the oracle perform -- at 3 fp64 instructions instead of ~12+ (tests/test_math.py checks 10^8 cases). */
-__device__ __forceinline__ double div_by(double n, double c, double rc) {
-  const double q0 = n * rc;
-  const double r = fma(-q0, c, n);
-  return fma(r, rc, q0);
-}
-
 #ifndef SLGPU_FAST_MINBLOCKS
 #define SLGPU_FAST_MINBLOCKS 2
 #endif
@@ -192,7 +183,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   const bool replay = (p.rng_mode == SLGPU_RNG_REPLAY);
   const int tid = threadIdx.x;
 
-  __shared__ double s_mn[D], s_mx[D], s_n0[D];
+  __shared__ double s_mn[D], s_mx[D], s_n0[D], s_rd[D];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
   /* dynamic shared memory (see fast_smem_bytes): three [D][NT] panels + the EPSR state of the block's stacks */
   extern __shared__ double s_dyn[];
@@ -212,6 +203,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     s_mn[i] = p.mn[i];
     s_mx[i] = p.mx[i];
     s_n0[i] = p.n0_diag[i];
+    s_rd[i] = 1.0 / (p.mx[i] - p.mn[i]);
   }
   for (int i = tid; i < T; i += NT) {
     s_w[3 * i + 0] = p.sig_w[3 * i + 0];
@@ -276,7 +268,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       /* GaussianProposal::propose (sampler.cpp:79-88): a_i = sum_{k<=i} fma(N_ik, z_k, .), k ascending */
       gemv_block<D, 0, kColBlock>(Lc, s_z + tid, NT, nscale, fresh, s_n0, a);
 #pragma unroll
-      for (int i = 0; i < D; ++i) a[i] = bounce1(s_x[i * NT + tid] + a[i] * sigma, s_mn[i], s_mx[i]);
+      for (int i = 0; i < D; ++i) a[i] = bounce1(s_x[i * NT + tid] + a[i] * sigma, s_mn[i], s_mx[i], s_rd[i]);
       /* energy = sum over job types in order (sampler.cpp:148-150) */
       double e_new = 0.0;
       if constexpr (StaticJobs<Lik, D>::value > 0) {

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NT, SLGPU_PAIR_MINBLOCKS) pt_step_pair_kernel(
   double* const s_epm = s_dyn + 3 * D * NCH + (D + 1) * NCH;
   double* const s_eps = s_epm + D * nsb;
   const int sb = (tid >> 5) * m.spw + m.sl;
-  __shared__ double s_mn[D], s_mx[D], s_n0[D];
+  __shared__ double s_mn[D], s_mx[D], s_n0[D], s_rd[D];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
   __shared__ double s_cnt[NCH], s_nsc[NCH];
   __shared__ u32 s_chain[NCH], s_owner[NCH];
@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(NT, SLGPU_PAIR_MINBLOCKS) pt_step_pair_kernel(
     s_mn[i] = p.mn[i];
     s_mx[i] = p.mx[i];
     s_n0[i] = p.n0_diag[i];
+    s_rd[i] = 1.0 / (p.mx[i] - p.mn[i]);
   }
   for (int i = tid; i < T; i += NT) {
     s_w[3 * i + 0] = p.sig_w[3 * i + 0];
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(NT, SLGPU_PAIR_MINBLOCKS) pt_step_pair_kernel(
       for (int mm = 0; mm < R; ++mm) {
         const int j = 2 * mm + g;
         if (j < D) {
-          a[mm] = bounce1(s_x[j * NCH + cb] + a[mm] * sigma, s_mn[j], s_mx[j]);
+          a[mm] = bounce1(s_x[j * NCH + cb] + a[mm] * sigma, s_mn[j], s_mx[j], s_rd[j]);
           xp[j] = a[mm];
         }
       }

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NT, SLGPU_QUAD_MINBLOCKS) pt_step_quad_kernel(
   double* const s_epm = s_f + NCH * JP;          /* EPSRDiagnostic M, [stack of block][D] */
   double* const s_eps = s_epm + nsb * D;
   const int sb = (tid >> 5) * m.spw + m.sl;
-  __shared__ double s_mn[D], s_mx[D], s_n0[D];
+  __shared__ double s_mn[D], s_mx[D], s_n0[D], s_rd[D];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
   __shared__ double s_cnt[NCH], s_nsc[NCH];
   __shared__ u32 s_owner[NCH];
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(NT, SLGPU_QUAD_MINBLOCKS) pt_step_quad_kernel(
     s_mn[i] = p.mn[i];
     s_mx[i] = p.mx[i];
     s_n0[i] = p.n0_diag[i];
+    s_rd[i] = 1.0 / (p.mx[i] - p.mn[i]);
   }
   for (int i = tid; i < T; i += NT) {
     s_w[3 * i + 0] = p.sig_w[3 * i + 0];
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(NT, SLGPU_QUAD_MINBLOCKS) pt_step_quad_kernel(
       for (int mm = 0; mm < R; ++mm) {
         const int j = 4 * mm + g;
         if (j < D) {
-          a[mm] = bounce1(x[mm] + a[mm] * sigma, s_mn[j], s_mx[j]);
+          a[mm] = bounce1(x[mm] + a[mm] * sigma, s_mn[j], s_mx[j], s_rd[j]);
           zv[j] = a[mm];
         }
       }

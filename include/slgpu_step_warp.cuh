@@ -63,12 +63,13 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
   double* const sw_u = sw + 2 * T;   /* [T] swap uniforms */
   double* const sw_x = sw + 3 * T;   /* [T][d] samples */
   int* const sw_acc = (int*)(s_dyn + (size_t)nwarps * (d + 1) + (size_t)nwarps * J + (size_t)spb * (3 * T + T * d)) + sl * T;
-  __shared__ double s_mn[SLGPU_MAX_DIMS], s_mx[SLGPU_MAX_DIMS], s_n0[SLGPU_MAX_DIMS];
+  __shared__ double s_mn[SLGPU_MAX_DIMS], s_mx[SLGPU_MAX_DIMS], s_n0[SLGPU_MAX_DIMS], s_rd[SLGPU_MAX_DIMS];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
   for (int i = tid; i < d; i += blockDim.x) {
     s_mn[i] = p.mn[i];
     s_mx[i] = p.mx[i];
     s_n0[i] = p.n0_diag[i];
+    s_rd[i] = 1.0 / (p.mx[i] - p.mn[i]);
   }
   for (int i = tid; i < T; i += blockDim.x) {
     s_w[3 * i + 0] = p.sig_w[3 * i + 0];
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       for (int m = 0; m < RM; ++m) {
         const int j = lane + 32 * m;
         if (j < d) {
-          a[m] = bounce1(x[m] + a[m] * sigma, s_mn[j], s_mx[j]);
+          a[m] = bounce1(x[m] + a[m] * sigma, s_mn[j], s_mx[j], s_rd[j]);
           vec[j] = a[m];
         }
       }
