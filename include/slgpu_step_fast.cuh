@@ -165,6 +165,95 @@ __device__ __forceinline__ double shaper_update_rolled(double* Lc, double* xs, i
   return prop_norm / smax(frob, eps);
 }
 
+/* ---- phase B with TWO lanes per staged chain: the update of one chain is a serial sequence of ~5600
+ * instructions, and a block waits for it every round, so its rows are split over a lane pair (lane h takes
+ * rows j = K0 + 2m + h of the column pair K0, K0+1); the column heads are computed by both lanes. ---- */
+template <int D, int K>
+__device__ __forceinline__ void shaper2_col(double* Lc, const double* col, double scale, int h, unsigned pm, double* xs, int xst,
+                                            double* fr, int fst) {
+  constexpr int K0 = K & ~1;                 /* first column of the pair this column belongs to */
+  constexpr int NM = (D - K0 + 1) / 2;       /* row slots per lane */
+  constexpr int TK = K * (K + 1) / 2;
+  const double eps = 1e-18;
+  const double xk = xs[K * xst];
+  const double Lkk = Lc[(TK + K) * kLs] * scale;
+  const double V = smax(eps, Lkk);
+  const double rV = 1.0 / V;
+  const double r = sqrt(V * V + xk * xk);
+  const double c = div_by(r, V, rV);
+  const double s = div_by(xk, V, rV);
+  const double rc = 1.0 / c;
+  __syncwarp(pm); /* both lanes have read the old diagonal and x_K */
+  if (h == (K & 1)) {
+    Lc[(TK + K) * kLs] = r;
+    fr[K * fst] = fma(r, r, fr[K * fst]); /* the diagonal closes row K's sum */
+  }
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const int j = K0 + 2 * m + h;
+    if (j > K && j < D) {
+      const int o = ((K0 + 2 * m) * (K0 + 2 * m + 1) / 2 + h * (K0 + 2 * m + 1) + K) * kLs;
+      const double xj = xs[j * xst];
+      double Ljk = col[m] * scale;
+      Ljk = div_by(Ljk + s * xj, c, rc);
+      Lc[o] = Ljk;
+      xs[j * xst] = c * xj - s * Ljk;
+      fr[j * fst] = fma(Ljk, Ljk, fr[j * fst]);
+    }
+  }
+  __syncwarp(pm); /* x_{K+1} is visible to the partner before the next head */
+}
+
+template <int D, int K0>
+__device__ __forceinline__ void shaper2_block(double* Lc, double scale, int h, unsigned pm, double* xs, int xst, double* fr, int fst) {
+  constexpr int NM = (D - K0 + 1) / 2;
+  constexpr bool two = (K0 + 1 < D);
+  double col0[NM], col1[NM];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) { /* both columns' rows of this lane first (in-triangle even where unused) */
+    const int j = K0 + 2 * m + h;
+    if (j < D) {
+      const int o = ((K0 + 2 * m) * (K0 + 2 * m + 1) / 2 + h * (K0 + 2 * m + 1) + K0) * kLs;
+      col0[m] = SLGPU_LDL(Lc + o);
+      if (two) col1[m] = SLGPU_LDL(Lc + o + kLs);
+    }
+  }
+  shaper2_col<D, K0>(Lc, col0, scale, h, pm, xs, xst, fr, fst);
+  if constexpr (two) shaper2_col<D, K0 + 1>(Lc, col1, scale, h, pm, xs, xst, fr, fst);
+  if constexpr (K0 + 2 < D) shaper2_block<D, K0 + 2>(Lc, scale, h, pm, xs, xst, fr, fst);
+}
+
+/* ProposalShaper::update by a lane pair; xs[j*xst] holds the accepted jump on entry, fr[j*fst] is scratch. */
+template <int D>
+__device__ __forceinline__ double shaper_update_pair2(double* Lc, double* xs, int xst, double* fr, int fst, double count,
+                                                      double prop_norm, int h, unsigned pm) {
+  const double eps = 1e-18;
+  const double sq = sqrt(count);
+  const double rsq = 1.0 / sq;
+  const double scale = sqrt((count - 1.0) / count);
+#pragma unroll
+  for (int i = h; i < D; i += 2) {
+    xs[i * xst] = div_by(xs[i * xst], sq, rsq);
+    fr[i * fst] = 0.0;
+  }
+  __syncwarp(pm);
+  shaper2_block<D, 0>(Lc, scale, h, pm, xs, xst, fr, fst);
+  /* |L|_F: slot l = row sum l (D <= 32), halving tree over 32 slots (both lanes, same result) */
+  double f[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) f[j] = fr[j * fst];
+  int nlive = D;
+#pragma unroll
+  for (int mm = 16; mm > 0; mm >>= 1) {
+#pragma unroll
+    for (int l = 0; l < mm; ++l)
+      if (l + mm < D && l + mm < nlive) f[l] += f[l + mm];
+    if (nlive > mm) nlive = mm;
+  }
+  const double frob = sqrt(f[0]);
+  return prop_norm / smax(frob, eps);
+}
+
 /* dynamic shared memory of pt_step_fast_kernel */
 template <int D, int NT>
 inline size_t fast_smem_bytes(unsigned n_temps) {
@@ -325,10 +414,22 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       const int slot = (tid >> 5) * per + (tid & 31);
       const bool mine = (tid & 31) < per && slot < nacc;
 #endif
+#ifndef SLGPU_PHASEB_PAIR /* measured on config #3: one lane per staged chain 59.7 us per round, a lane pair 68.8 */
       if (mine) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
         s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
                                                        s_cnt[slot], p.prop_norm);
       }
+#else
+      (void)mine;
+      /* a lane pair per staged chain (threads 2u, 2u+1 take slot u, u + NT/2, ...): jump in s_jump[.][u], row sums
+       * in column u of s_z (every z is dead by now) */
+      const unsigned pm = 3u << (m.lane & ~1);
+      for (int u = tid >> 1; u < nacc; u += NT / 2) {
+        const double ns = shaper_update_pair2<D>(l_base(p.L, s_chain[u], D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
+                                                 p.prop_norm, tid & 1, pm);
+        if ((tid & 1) == 0) s_nsc[s_owner[u]] = ns;
+      }
+#endif
       if (tid == 0) s_nacc[par ^ 1] = 0;
     }
     __syncthreads();
@@ -395,27 +496,33 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
       lg_att += (swap_type != 0);
-      if (m.t == 0) {
-        const double nn = (double)(r + 1);
-        const double rnn = 1.0 / nn;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const int o = i * nsb + sb;
+      if (m.t == 0 && p.rows_out) { /* the five scalar fields of the cold row (db.cpp:18-25) */
+        double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (D + SLGPU_ROW_EXTRA);
+        row[D] = energy;
+        row[D + 1] = row_sigma;
+        row[D + 2] = row_beta;
+        row[D + 3] = (double)accepted;
+        row[D + 4] = (double)swap_type;
+      }
+    }
+    /* EPSRDiagnostic::update (diagnostics.cpp:27-47) and the sample fields of the cold rows: the (cold chain,
+     * dimension) pairs of this warp are dealt to all 32 lanes instead of 20 dimensions on each of the few cold lanes */
+    __syncwarp();
+    {
+      const double nn = (double)(r + 1);
+      const double rnn = 1.0 / nn;
+      const u32 s0 = (blockIdx.x * (NT / 32) + (u32)(tid >> 5)) * (u32)m.spw; /* first stack of this warp */
+      for (int task = m.lane; task < m.spw * D; task += 32) {
+        const int sl = task / D, i = task - sl * D;
+        const u32 sc = s0 + (u32)sl;
+        if (sc < p.n_stacks) {
+          const int o = i * nsb + (tid >> 5) * m.spw + sl;
           const double mo = s_epm[o];
-          const double xi = s_x[i * NT + tid];
+          const double xi = s_x[i * NT + (tid & ~31) + sl * T];
           const double newM = mo + div_by(xi - mo, nn, rnn);
           s_eps[o] = s_eps[o] + (xi - mo) * (xi - newM);
           s_epm[o] = newM;
-        }
-        if (p.rows_out) {
-          double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (D + SLGPU_ROW_EXTRA);
-#pragma unroll
-          for (int i = 0; i < D; ++i) row[i] = s_x[i * NT + tid];
-          row[D] = energy;
-          row[D + 1] = row_sigma;
-          row[D + 2] = row_beta;
-          row[D + 3] = (double)accepted;
-          row[D + 4] = (double)swap_type;
+          if (p.rows_out) p.rows_out[((size_t)it * p.n_stacks + sc) * (D + SLGPU_ROW_EXTRA) + i] = xi;
         }
       }
     }
