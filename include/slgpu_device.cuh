@@ -35,6 +35,9 @@
 #include <string.h>
 
 #include <type_traits>
+#ifdef SLGPU_TIMING
+#include <cstdio>
+#endif
 
 #include "slgpu_math.h"
 #include "slgpu_plugin.h"

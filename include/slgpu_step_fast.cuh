@@ -254,6 +254,13 @@ __device__ __forceinline__ double shaper_update_pair2(double* Lc, double* xs, in
   return prop_norm / smax(frob, eps);
 }
 
+/* chain of thread slot ct of this block under ThreadMap (only called for active slots) */
+__device__ __forceinline__ u32 thread_chain(const slgpu_step_params& p, int ct) {
+  const int T = (int)p.n_temps, spw = 32 / T, lane = ct & 31, sl = lane / T, t = lane - sl * T;
+  const u32 s = (blockIdx.x * (blockDim.x >> 5) + (u32)(ct >> 5)) * (u32)spw + (u32)sl;
+  return s * (u32)T + (u32)t;
+}
+
 /* dynamic shared memory of pt_step_fast_kernel */
 template <int D, int NT>
 inline size_t fast_smem_bytes(unsigned n_temps) {
@@ -285,8 +292,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   const int sb = (tid >> 5) * m.spw + m.sl;  /* this thread's stack within the block */
   __shared__ double s_cnt[NT];      /* shaper count (already incremented) of the staged chain */
   __shared__ double s_nsc[NT];      /* result: new N scale, indexed by owning thread */
-  __shared__ u32 s_chain[NT];       /* chain id of the staged chain */
-  __shared__ u32 s_owner[NT];       /* owning thread of the staged chain */
+  __shared__ unsigned short s_owner[NT]; /* owning thread of the staged chain (its chain id follows from the thread map) */
   __shared__ int s_nacc[2];
   for (int i = tid; i < D; i += NT) {
     s_mn[i] = p.mn[i];
@@ -384,8 +390,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
           s_x[i * NT + tid] = nx;
         }
         s_cnt[slot] = sh_count;
-        s_chain[slot] = c;
-        s_owner[slot] = (u32)tid;
+        s_owner[slot] = (unsigned short)tid;
         energy = e_new;
         row_sigma = sigma;
         row_beta = beta;
@@ -416,8 +421,9 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #endif
 #ifndef SLGPU_PHASEB_PAIR /* measured on config #3: one lane per staged chain 59.7 us per round, a lane pair 68.8 */
       if (mine) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
-        s_nsc[s_owner[slot]] = shaper_update_rolled<D>(l_base(p.L, s_chain[slot], D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
-                                                       s_cnt[slot], p.prop_norm);
+        const int own = s_owner[slot];
+        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, own), D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
+                                             s_cnt[slot], p.prop_norm);
       }
 #else
       (void)mine;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
        * in column u of s_z (every z is dead by now) */
       const unsigned pm = 3u << (m.lane & ~1);
       for (int u = tid >> 1; u < nacc; u += NT / 2) {
-        const double ns = shaper_update_pair2<D>(l_base(p.L, s_chain[u], D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
+        const double ns = shaper_update_pair2<D>(l_base(p.L, thread_chain(p, s_owner[u]), D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
                                                  p.prop_norm, tid & 1, pm);
         if ((tid & 1) == 0) s_nsc[s_owner[u]] = ns;
       }
