@@ -280,7 +280,8 @@ def main():
             e.step_rounds(R)
         e.sync()                  # includes the D2H copies of the last segments
         spans = e.peek()          # the result of the last step, read on the host
-        checksum = float(sum(float(s[:, d].sum()) for s in spans))
+        last = spans[-1][-S:] if spans else np.zeros((0, d + 5))  # the rows of the last round: the result the host reads
+        checksum = float(last[:, d].sum())
         t1 = time.perf_counter()
         barrier()
         e2e_s = max_over_ranks(t1 - t0)
