@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.005)
+            self._halt.wait(0.001)
 
     def finish(self):
         self._halt.set()
