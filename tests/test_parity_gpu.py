@@ -150,3 +150,40 @@ def test_use_initial():
         assert np.array_equal(rows0[:, :4], np.tile(init, (w["S"], 1)))
         eng.step_rounds(29)
         assert np.array_equal(eng.last_rows(), orc.last_rows())
+
+
+EDGE_SHAPES = [
+    # S, T, d, J, rounds: smallest sizes, single temperature, ladders that fill a warp, ragged lane maps,
+    # dimensions around the kernel boundaries (32 | 33: thread-per-chain vs warp-per-chain; 64 | 65 | 96 | 97: row groups)
+    (1, 1, 1, 1, 25), (3, 1, 2, 2, 25), (2, 32, 3, 1, 31), (5, 3, 5, 4, 31), (3, 7, 32, 3, 21), (3, 7, 33, 3, 21),
+    (2, 5, 64, 40, 15), (2, 9, 65, 2, 15), (1, 16, 97, 5, 12), (1, 32, 128, 1, 11),
+]
+
+
+@pytest.mark.parametrize("S,T,d,J,rounds", EDGE_SHAPES)
+def test_edge_shapes_bit_exact(S, T, d, J, rounds):
+    """Edge shapes through the generic likelihood (demo Gaussian accepts any d and J): every kernel family
+    (thread-per-chain runtime-d, warp-per-chain with 2 / 3 / 4 row groups) against the oracle, bit for bit."""
+    mn = [-3.0 - 0.1 * i for i in range(d)]
+    mx = [2.0 + 0.2 * i for i in range(d)]
+    w = dict(S=S, T=T, d=d, J=J, mn=mn, mx=mx, swapInterval=4, optAccept=0.3, optSwap=0.35, plugin="demo_gauss", payload=None,
+             oracle_target=configs.T_DEMO_GAUSS, oracle_params=None)
+    orc = oracle_for(w, seed=5, stack_offset=3)
+    orc.init_chains()
+    orc.run_rounds(rounds)
+    with engine_for(w, seed=5, stack_offset=3) as eng:
+        eng.init_chains()
+        eng.step_rounds(rounds)
+        _compare(eng, orc, w, "edge shape S=%d T=%d d=%d J=%d" % (S, T, d, J))
+        rows = eng.drain().reshape(rounds + 1, S, d + 5)
+        for s in range(S):
+            assert np.array_equal(rows[:, s], orc.cold_rows(s))
+
+
+def test_zero_rounds_and_empty_run():
+    w = configs.workload("config1")
+    with engine_for(w, seed=1) as eng:
+        eng.init_chains()
+        eng.step_rounds(0)
+        assert eng.rounds_done == 0
+        assert eng.drain().shape == (w["S"], w["d"] + 5)  # only the initial rows
