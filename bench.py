@@ -208,8 +208,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    bound_cpus = None
     if world > 1:
         import torch.distributed as dist
+        from stateline_b200.dist import bind_to_gpu_cpus
+        bound_cpus = bind_to_gpu_cpus(local_rank)  # pinned row ring on the GPU's own NUMA node
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -332,7 +335,7 @@ def main():
         "data": "synthetic", "config": bench_config(T, d, J, S), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h_per_step),
                 "note": "inputs are the resident chain state and on-device Philox draws: nothing to upload per step; every cold-chain row is copied D2H to pinned memory inside the timed region",
-                "checksum": checksum},
+                "checksum": checksum, "host_cpus_bound": (len(bound_cpus) if bound_cpus else None)},
         "gpu_launches": int(launches), "roofline": roofline,
         "job_evals_per_sec": value * J, "cold_samples_per_sec": value / T,
         "diagnostics": {"rhat_mean": float(np.mean(rhat)), "rhat_max": float(np.max(rhat)),

@@ -4,9 +4,51 @@ Stacks never exchange state (src/infer/sampler.cpp:173 swaps only id <-> id+1 in
 stacks [g*S/G, (g+1)*S/G) with its own tier models -- the same thing as G stateline servers each running
 S/G stacks.  The only collectives are the end-of-run diagnostics below (two small all-reduces for R-hat, one
 for the counters), issued through torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests)."""
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_cpus(device_index):
+    """Pin this process (and the threads it spawns later: the engine's drain thread) to the host cores next to
+    GPU `device_index`, so that the pinned row ring is first-touched on the GPU's own NUMA node and the D2H
+    row stream does not cross the socket interconnect.  Call it before creating the engine.  Returns the
+    core set applied, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            tok = visible.split(",")[device_index].strip()
+            h = pynvml.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:], rest)
+        with open(path) as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def shard_stacks(total_stacks, rank, world):

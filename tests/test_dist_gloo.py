@@ -75,3 +75,15 @@ def test_two_rank_rhat_matches_union(tmp_path):
     assert np.allclose(got[:4], want, rtol=1e-12)
     acc = sum(s.counters()["accepts"].reshape(-1, 4).sum(0) for s in shards) / sum(s.counters()["length"].reshape(-1, 4).sum(0) for s in shards)
     assert np.allclose(got[4:8], acc, rtol=1e-12)
+
+
+def test_cpulist_parse_and_bind_is_harmless_without_gpu():
+    import os
+    from stateline_b200.dist import _parse_cpulist, bind_to_gpu_cpus
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("\n") == set()
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu_cpus(0)
+    assert got is None or got <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
