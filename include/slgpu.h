@@ -133,6 +133,18 @@ void slgpu_rhat_finish(const double* sum_dm2, const double* sum_s, double n_stac
 /* end-of-run summary as JSON: per-tier accept / swap rates, sigma, beta, R-hat, rounds, rows */
 slgpu_status slgpu_summary(slgpu_engine* e, char* json, size_t cap, size_t* needed);
 
+/* Checkpoint / resume.  The reference declares ChainArray::recoverFromDisk (src/infer/chainarray.hpp:158-162) and
+ * never defines it, so a stateline run cannot be resumed; this is the device-side equivalent.  slgpu_save_state
+ * waits for the rounds issued so far and writes every chain's state (sample, energy, sigma, beta, shaper factor,
+ * counters), the tier models, the ladder, the pending regression statistics, the R-hat accumulators and the
+ * round counter to `path` (written to path.tmp, then renamed).  slgpu_load_state restores them into an engine
+ * created from the same configuration and plugin (SLGPU_E_CONFIG otherwise; SLGPU_E_IO for a missing, foreign or
+ * truncated file, which leaves the engine untouched); it replaces slgpu_init_chains.  The random streams are
+ * addressed by round index, so a resumed run continues bit for bit.  Rows emitted before the checkpoint are not
+ * emitted again; with sink "csv" create the resuming engine with "gpu": {"append": true}. */
+slgpu_status slgpu_save_state(slgpu_engine* e, const char* path);
+slgpu_status slgpu_load_state(slgpu_engine* e, const char* path);
+
 /* contract check: nll[point*J + job] = f(job, x[point*d ..]) through the plugin's functor (host buffers) */
 slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_points, double* nll);
 /* one State row as CSVChainArrayWriter prints it (db.cpp:18-25), no newline; returns the length */

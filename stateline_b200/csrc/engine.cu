@@ -68,6 +68,7 @@ struct Settings {
   uint32_t adaptInterval = 0, maxRoundsPerLaunch = 64;
   uint64_t hostRingRounds = 0;
   bool overwrite = false;
+  bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
 };
 
 struct Segment {
@@ -79,6 +80,13 @@ struct Segment {
 struct PendingCopy {
   cudaEvent_t ev;
   uint64_t rows_end;
+};
+
+// one device array of the sampler state, as written to / read from a checkpoint
+struct StateBuf {
+  const char* name;
+  void* dev;
+  size_t bytes;
 };
 
 }  // namespace
@@ -94,6 +102,7 @@ struct slgpu_engine {
   double step_kernel_ms = 0.0;
   uint64_t step_kernel_launches = 0;
   std::vector<void*> allocs;
+  std::vector<StateBuf> state;         // everything a resumed run needs (slgpu_save_state / slgpu_load_state)
   slgpu_step_params P{};
   double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
   void* d_payload = nullptr;
@@ -188,6 +197,7 @@ Settings parse_settings(const char* text) {
     if (g->find("maxRoundsPerLaunch")) s.maxRoundsPerLaunch = (uint32_t)need_uint(*g, "maxRoundsPerLaunch");
     if (g->find("hostRingRounds")) s.hostRingRounds = need_uint(*g, "hostRingRounds");
     if (g->find("overwrite")) s.overwrite = need(*g, "overwrite", slgpu_json::Value::Bool).b;
+    if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
     if (g->find("rng")) {
       const std::string& r = need(*g, "rng", slgpu_json::Value::String).str;
       if (r == "philox") s.rng = SLGPU_RNG_PHILOX;
@@ -529,6 +539,17 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     TRY_ST(dev_alloc(e, &e->d_sums, (size_t)2 * T * 9));
     P.sig_w = e->d_sig_w;
     P.ladder = e->d_ladder;
+    {
+      const size_t nLall = nL * ((C + SLGPU_L_TILE - 1) / SLGPU_L_TILE) * SLGPU_L_TILE, f8 = sizeof(double), i4 = sizeof(int32_t);
+      e->state = {{"x", P.x, d * C * f8}, {"L", P.L, nLall * f8}, {"energy", P.energy, C * f8}, {"row_sigma", P.row_sigma, C * f8},
+                  {"row_beta", P.row_beta, C * f8}, {"sigma", P.sigma, C * f8}, {"beta", P.beta, C * f8}, {"nscale", P.nscale, C * f8},
+                  {"sh_count", P.sh_count, C * f8}, {"accepted", P.accepted, C * i4}, {"swap_type", P.swap_type, C * i4},
+                  {"lg_accepts", P.lg_accepts, C * i4}, {"lg_swaps", P.lg_swaps, C * i4}, {"lg_swap_attempts", P.lg_swap_attempts, C * i4},
+                  {"lg_min_energy", P.lg_min_energy, C * f8}, {"p_sig", P.p_sig, 9 * C * f8}, {"p_beta", P.p_beta, 9 * C * f8},
+                  {"ep_m", P.ep_m, (size_t)d * S * f8}, {"ep_s", P.ep_s, (size_t)d * S * f8},
+                  {"models", e->d_models, (size_t)2 * T * slgpu_tier::kModelStride * f8}, {"sig_w", e->d_sig_w, (size_t)3 * T * f8},
+                  {"ladder", e->d_ladder, T * f8}};
+    }
     if (payload && payload_bytes) {
       TRY_ST(dev_alloc(e, (char**)&e->d_payload, payload_bytes));
       CU_TRY(cudaMemcpy(e->d_payload, payload, payload_bytes, cudaMemcpyHostToDevice));
@@ -557,7 +578,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
       mkdir(cfg.outputPath.c_str(), 0777);
       e->csv_buf.assign(S, std::string());
       for (uint32_t s = 0; s < S; ++s) {
-        std::ofstream f(csv_path(e, s), std::ios::trunc);
+        std::ofstream f(csv_path(e, s), cfg.append ? std::ios::app : std::ios::trunc);
         if (!f.good()) return fail(SLGPU_E_IO, "cannot create " + csv_path(e, s));
       }
     }
@@ -1052,6 +1073,124 @@ slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_
   cudaFree(dn);
   e->launches++;
   if (err != cudaSuccess) return fail(SLGPU_E_CUDA, std::string("eval: ") + cudaGetErrorString(err));
+  return SLGPU_OK;
+}
+
+
+// ---------------------------------------------------------------- checkpoint / resume
+// The reference declares ChainArray::recoverFromDisk (src/infer/chainarray.hpp:158-162) but never defines it; a
+// stateline run cannot be resumed.  Here the whole sampler state is a handful of device arrays plus the round
+// counter (the Philox streams are addressed by round index, so there is no generator state to save), and a
+// resumed run continues bit for bit.
+namespace {
+
+struct CkHeader {
+  char magic[8];
+  uint32_t version, n_stacks, n_temps, n_dims, n_job_types, swap_interval, adapt_interval, stack_offset, l_layout, rng;
+  uint32_t n_sections, reserved;
+  uint64_t seed, rounds_done, bounds_hash;
+  double opt_accept, opt_swap;
+  char plugin[32];
+};
+struct CkSection {
+  char name[24];
+  uint64_t bytes;
+};
+constexpr char kCkMagic[8] = {'S', 'L', 'G', 'P', 'U', 'C', 'K', '1'};
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
+CkHeader ck_header(const slgpu_engine* e) {
+  CkHeader h;
+  std::memset(&h, 0, sizeof h);
+  std::memcpy(h.magic, kCkMagic, 8);
+  const Settings& c = e->cfg;
+  h.version = 1;
+  h.n_stacks = c.nStacks; h.n_temps = c.nTemps; h.n_dims = c.nDims; h.n_job_types = c.nJobTypes;
+  h.swap_interval = c.swapInterval; h.adapt_interval = c.adaptInterval; h.stack_offset = c.stackOffset;
+  h.l_layout = SLGPU_L_LAYOUT(c.nDims); h.rng = (uint32_t)c.rng;
+  h.n_sections = (uint32_t)e->state.size();
+  h.seed = c.seed;
+  h.rounds_done = e->rounds_done;
+  uint64_t bh = 0xcbf29ce484222325ull;
+  bh = fnv1a(c.mn.data(), c.mn.size() * sizeof(double), bh);
+  bh = fnv1a(c.mx.data(), c.mx.size() * sizeof(double), bh);
+  h.bounds_hash = bh;
+  h.opt_accept = c.optimalAcceptRate; h.opt_swap = c.optimalSwapRate;
+  std::strncpy(h.plugin, e->plug->name ? e->plug->name : "", sizeof h.plugin - 1);
+  return h;
+}
+
+struct FileCloser {
+  FILE* f;
+  ~FileCloser() { if (f) std::fclose(f); }
+};
+
+}  // namespace
+
+slgpu_status slgpu_save_state(slgpu_engine* e, const char* path) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if (!path || !path[0]) return fail(SLGPU_E_ARG, "path must not be empty");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const std::string tmp = std::string(path) + ".tmp";
+  {
+    FileCloser fc{std::fopen(tmp.c_str(), "wb")};
+    if (!fc.f) return fail(SLGPU_E_IO, "cannot create " + tmp);
+    const CkHeader h = ck_header(e);
+    bool ok = std::fwrite(&h, sizeof h, 1, fc.f) == 1;
+    std::vector<char> host;
+    for (const StateBuf& b : e->state) {
+      CkSection sec;
+      std::memset(&sec, 0, sizeof sec);
+      std::strncpy(sec.name, b.name, sizeof sec.name - 1);
+      sec.bytes = b.bytes;
+      host.resize(b.bytes);
+      CU_TRY(cudaMemcpy(host.data(), b.dev, b.bytes, cudaMemcpyDeviceToHost));
+      ok = ok && std::fwrite(&sec, sizeof sec, 1, fc.f) == 1 && (b.bytes == 0 || std::fwrite(host.data(), b.bytes, 1, fc.f) == 1);
+    }
+    ok = ok && std::fflush(fc.f) == 0;
+    if (!ok) {
+      std::remove(tmp.c_str());
+      return fail(SLGPU_E_IO, "short write to " + tmp);
+    }
+  }
+  if (std::rename(tmp.c_str(), path) != 0) return fail(SLGPU_E_IO, std::string("cannot rename ") + tmp + " to " + path);
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!path || !path[0]) return fail(SLGPU_E_ARG, "path must not be empty");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  FileCloser fc{std::fopen(path, "rb")};
+  if (!fc.f) return fail(SLGPU_E_IO, std::string("cannot open ") + path);
+  CkHeader h;
+  if (std::fread(&h, sizeof h, 1, fc.f) != 1 || std::memcmp(h.magic, kCkMagic, 8) != 0 || h.version != 1)
+    return fail(SLGPU_E_IO, std::string(path) + " is not a slgpu checkpoint");
+  CkHeader want = ck_header(e);
+  want.rounds_done = h.rounds_done;
+  if (std::memcmp(&h, &want, sizeof h) != 0)
+    return fail(SLGPU_E_CONFIG, std::string(path) + " was written by a run with a different configuration (shape, bounds, seed, rates or plugin)");
+  // read everything before touching the device: a truncated file must leave the engine as it was
+  std::vector<std::vector<char>> data(e->state.size());
+  for (size_t i = 0; i < e->state.size(); ++i) {
+    const StateBuf& b = e->state[i];
+    CkSection sec;
+    if (std::fread(&sec, sizeof sec, 1, fc.f) != 1 || std::strncmp(sec.name, b.name, sizeof sec.name) != 0 || sec.bytes != b.bytes)
+      return fail(SLGPU_E_IO, std::string(path) + ": section " + b.name + " is missing or has the wrong size");
+    data[i].resize(b.bytes);
+    if (b.bytes && std::fread(data[i].data(), b.bytes, 1, fc.f) != 1) return fail(SLGPU_E_IO, std::string(path) + " is truncated");
+  }
+  for (size_t i = 0; i < e->state.size(); ++i)
+    CU_TRY(cudaMemcpy(e->state[i].dev, data[i].data(), e->state[i].bytes, cudaMemcpyHostToDevice));
+  e->rounds_done = h.rounds_done;
+  e->initialised = true;
   return SLGPU_OK;
 }
 

@@ -29,6 +29,7 @@ SYMBOLS = [
     "slgpu_get_sigma_beta", "slgpu_get_shaper", "slgpu_get_models", "slgpu_get_ladder",
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
+    "slgpu_save_state", "slgpu_load_state",
 ]
 
 BUILTIN_ENTRIES = {
@@ -98,6 +99,8 @@ def lib():
     L.slgpu_format_row.argtypes = [_dp, C.c_uint32, C.c_char_p, C.c_size_t]
     L.slgpu_format_row.restype = C.c_size_t
     L.slgpu_measure_fp64_peak.argtypes = [C.c_int, _dp]
+    L.slgpu_save_state.argtypes = [C.c_void_p, C.c_char_p]
+    L.slgpu_load_state.argtypes = [C.c_void_p, C.c_char_p]
     _lib = L
     return L
 
@@ -204,6 +207,14 @@ class Engine:
 
     def run(self):
         _check(lib().slgpu_run(self.h))
+
+    def save_state(self, path):
+        """Checkpoint every chain, the tier models and the round counter (slgpu_save_state)."""
+        _check(lib().slgpu_save_state(self.h, os.fspath(path).encode()))
+
+    def load_state(self, path):
+        """Resume from a checkpoint written by an engine with the same config and plugin; replaces init_chains."""
+        _check(lib().slgpu_load_state(self.h, os.fspath(path).encode()))
 
     @property
     def rounds_done(self):

@@ -202,3 +202,113 @@ def test_user_plugin_and_cpp_host(tmp_path):
     summ = json.loads(out.decode().strip().splitlines()[-1])
     assert summ["rounds"] == 100
     assert len(open(os.path.join(c2["outputPath"], "1.csv")).read().splitlines()) == 101
+
+
+def _full_state(eng, chains):
+    sig, beta = eng.sigma_beta()
+    out = [eng.last_rows(), sig, beta, eng.ladder(), eng.rhat()]
+    for which in (0, 1):
+        out += list(eng.models(which))
+    c = eng.counters()
+    out += [c[k] for k in sorted(c)]
+    for ch in chains:
+        out += list(eng.shaper(ch))
+    return [np.asarray(v) for v in out]
+
+
+@pytest.mark.parametrize("name,S,cut", [("config3", 16, 17), ("config3", 16, 19), ("config4", 4, 8), ("config2", 8, 1)])
+def test_checkpoint_resume_is_bit_exact(tmp_path, name, S, cut):
+    """slgpu_save_state / slgpu_load_state (the recoverFromDisk the reference declares at chainarray.hpp:158-162
+    and never defines): a run cut at any round -- inside a swap interval, or right before the adapt round (19,
+    where the tier statistics of 9 rounds are pending) -- and resumed in a fresh engine gives the same bits as
+    the uninterrupted run: rows, chain state, shaper factors, tier models, ladder, counters and R-hat."""
+    w = configs.workload(name, S=S)
+    total = 41
+    chains = [0, 1, w["T"], S * w["T"] - 1]
+    with engine_for(w, seed=21) as eng:
+        eng.init_chains()
+        eng.step_rounds(total)
+        want_rows, want_state = eng.drain(), _full_state(eng, chains)
+    ck = tmp_path / "state.slgpu"
+    with engine_for(w, seed=21) as eng:
+        eng.init_chains()
+        eng.step_rounds(cut)
+        eng.save_state(ck)
+        head = eng.drain()
+        eng.step_rounds(3)  # the checkpoint is a snapshot: the donor carries on unharmed
+    assert not os.path.exists(str(ck) + ".tmp")
+    with engine_for(w, seed=21) as eng:
+        eng.load_state(ck)
+        assert eng.rounds_done == cut
+        eng.step_rounds(total - cut)
+        tail = eng.drain()
+        got_state = _full_state(eng, chains)
+    assert np.array_equal(np.concatenate([head, tail]), want_rows)
+    for a, b in zip(got_state, want_state):
+        assert np.array_equal(a, b)
+
+
+def test_checkpoint_rejects_foreign_and_damaged_files(tmp_path):
+    w = configs.workload("config1")
+    ck = tmp_path / "a.slgpu"
+    with engine_for(w, seed=3) as eng:
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.save_state(ck)  # nothing to save before the chains exist
+        assert ei.value.status == engine.E_STATE
+        eng.init_chains()
+        eng.step_rounds(12)
+        eng.save_state(ck)
+        before = eng.last_rows()
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.load_state(tmp_path / "missing.slgpu")
+        assert ei.value.status == engine.E_IO
+        blob = open(ck, "rb").read()
+        open(tmp_path / "cut.slgpu", "wb").write(blob[: len(blob) // 2])
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.load_state(tmp_path / "cut.slgpu")
+        assert ei.value.status == engine.E_IO
+        open(tmp_path / "junk.slgpu", "wb").write(b"x" * 4096)
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.load_state(tmp_path / "junk.slgpu")
+        assert ei.value.status == engine.E_IO
+        assert np.array_equal(eng.last_rows(), before) and eng.rounds_done == 12  # failed loads change nothing
+    for other in (dict(seed=4), dict(seed=3, stack_offset=2)):
+        with engine_for(w, **other) as eng:
+            with pytest.raises(sb.SlgpuError) as ei:
+                eng.load_state(ck)
+            assert ei.value.status == engine.E_CONFIG
+    w2 = configs.workload("config2", S=2)
+    with engine_for(w2, seed=3) as eng:
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.load_state(ck)
+        assert ei.value.status == engine.E_CONFIG
+
+
+def test_csv_resume_appends(tmp_path):
+    """A run checkpointed and resumed with "gpu": {"append": true} leaves the same <stack>.csv files as one run."""
+    w = configs.workload("config1")
+
+    def cfg_for(out, **gpu):
+        cfg = configs.engine_config(w, sink="csv", seed=4, **gpu)
+        cfg["outputPath"] = str(tmp_path / out)
+        return cfg
+
+    cfg = cfg_for("whole")
+    cfg["nSamplesTotal"] = 2 * 50
+    with Engine(cfg, plugin=w["plugin"]) as eng:
+        eng.run()
+    ck = tmp_path / "mid.slgpu"
+    cfg = cfg_for("parts")
+    cfg["nSamplesTotal"] = 2 * 23
+    with Engine(cfg, plugin=w["plugin"]) as eng:
+        eng.run()
+        eng.save_state(ck)
+    cfg = cfg_for("parts", append=True)
+    cfg["nSamplesTotal"] = 2 * 50
+    with Engine(cfg, plugin=w["plugin"]) as eng:
+        eng.load_state(ck)
+        eng.run()
+    for s in range(w["S"]):
+        a = open(tmp_path / "whole" / ("%d.csv" % s)).read()
+        b = open(tmp_path / "parts" / ("%d.csv" % s)).read()
+        assert a == b and a.count("\n") == 51
