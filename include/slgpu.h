@@ -133,6 +133,16 @@ void slgpu_rhat_finish(const double* sum_dm2, const double* sum_s, double n_stac
 /* end-of-run summary as JSON: per-tier accept / swap rates, sigma, beta, R-hat, rounds, rows */
 slgpu_status slgpu_summary(slgpu_engine* e, char* json, size_t cap, size_t* needed);
 
+/* TableLogger (src/infer/logging.cpp:35-87).  slgpu_get_logger returns, per chain, energies_ (the energy of the last
+ * state the logger saw) and the adapters' windowed accept / swap rates (RegressionAdapter::rates(),
+ * adaptive.cpp:80-90: the AcptRt and SwapRt columns); the rates need "gpu": {"windowRates": true} (SLGPU_E_STATE
+ * otherwise; any of the three pointers may be NULL).  slgpu_format_table renders the table the reference prints
+ * every loggingRateSec -- ID, Length, MinEngy, CurrEngy, Sigma, AcptRt, GlbAcptRt, Beta, SwapRt, GlbSwapRt, a blank
+ * line between stacks -- followed by its "Convergence test: <mean R-hat> (not converged|possibly converged)" line,
+ * from a snapshot of the device counters.  *needed = bytes including the terminator. */
+slgpu_status slgpu_get_logger(slgpu_engine* e, double* cur_energy, double* accept_rate, double* swap_rate);
+slgpu_status slgpu_format_table(slgpu_engine* e, char* out, size_t cap, size_t* needed);
+
 /* Checkpoint / resume.  The reference declares ChainArray::recoverFromDisk (src/infer/chainarray.hpp:158-162) and
  * never defines it, so a stateline run cannot be resumed; this is the device-side equivalent.  slgpu_save_state
  * waits for the rounds issued so far and writes every chain's state (sample, energy, sigma, beta, shaper factor,

@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
   p.lg_swaps[c] = 0;
   p.lg_swap_attempts[c] = 1;
   p.lg_min_energy[c] = __longlong_as_double(0x7ff0000000000000LL);
+  p.lg_cur_energy[c] = 0.0; /* energies_ is a zero-filled vector until the first update (logging.cpp:23) */
   for (int k = 0; k < 9; ++k) {
     p.p_sig[pidx(p, k, m.t, m.s)] = 0.0;
     p.p_beta[pidx(p, k, m.t, m.s)] = 0.0;
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
   const int W = (int)p.swap_interval;
 
   for (u32 it = 0; it < p.n_rounds; ++it) {
+    bool mh_acc = false; /* this chain's own Metropolis-Hastings decision of the round */
     const u64 r = p.round_begin + it;
     if (active) {
       /* ---- proposal: x' = bounce(x + N z sigma), GaussianProposal::propose sampler.cpp:79-93 ---- */
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
         row_beta = beta;
       }
       accepted = acc ? 1 : 0;
+      mh_acc = acc;
       swap_type = 0;
       /* ---- sigma adaptation, sampler.cpp:160-162 (statistics summed, model frozen) ---- */
       const double logtemper = -slm_log(row_beta);
@@ -492,6 +495,8 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
       lg_att += (swap_type != 0);
+      if (p.round_flags) p.round_flags[(size_t)it * C + c] = (unsigned char)((mh_acc ? 1 : 0) | (swap_type << 1));
+      if (it + 1 == p.n_rounds) p.lg_cur_energy[c] = mid_e; /* TableLogger energies_ (logging.cpp:43) */
       if (m.t == 0) {
         /* ---- EPSRDiagnostic::update diagnostics.cpp:27-47; n_ counts the cold rows seen ---- */
         const double nn = (double)(r + 1);

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SLGPU_PLUGIN_ABI 1u
+#define SLGPU_PLUGIN_ABI 2u
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
 #define SLGPU_L_TILE 128u   /* chains per tile of the packed-L store (see slgpu_step_params.L) */
@@ -77,6 +77,11 @@ typedef struct slgpu_step_params {
   uint32_t* lg_swaps;
   uint32_t* lg_swap_attempts;
   double* lg_min_energy;
+  double* lg_cur_energy;   /* energy of the last state the logger saw (mid-sweep on swap rounds, logging.cpp:43) */
+  /* optional per-round log for the windowed rates of the table logger (RegressionAdapter::rates_, adaptive.cpp:80-90):
+   * round_flags[(round - round_begin) * C + chain] = bit 0: this chain's proposal was accepted that round,
+   * bits 1-2: swapType of the pair (chain, chain+1) that round.  NULL = not wanted. */
+  unsigned char* round_flags;
   /* tier models, frozen while a launch runs */
   const double* sig_w;     /* [T][3] weights of the sigma regression */
   const double* ladder;    /* [T] beta ladder from the last adapt point */

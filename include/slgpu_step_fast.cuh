@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     }
     __syncthreads();
     if (acc) nscale = s_nsc[tid];
+    /* the table logger's per-round log: written here, where acc dies; the swap sweep below adds its two bits */
+    if (p.round_flags && active) p.round_flags[(size_t)it * C + c] = (unsigned char)(acc ? 1 : 0);
 
     /* ================= swap sweep, hottest pair first ================= */
     double mid_e = energy;
@@ -487,6 +489,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       accepted = new_acc;
       if (active && m.t < T - 1) {
         swap_type = my_swapped ? 1 : 2;
+        if (p.round_flags) p.round_flags[(size_t)it * C + c] |= (unsigned char)(swap_type << 1);
         double Pb[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) Pb[k] = p.p_beta[pidx(p, k, m.t, m.s)];
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
       lg_att += (swap_type != 0);
+      if (it + 1 == p.n_rounds) p.lg_cur_energy[c] = mid_e; /* TableLogger energies_ (logging.cpp:43) */
       if (m.t == 0 && p.rows_out) { /* the five scalar fields of the cold row (db.cpp:18-25) */
         double* row = p.rows_out + ((size_t)it * p.n_stacks + m.s) * (D + SLGPU_ROW_EXTRA);
         row[D] = energy;

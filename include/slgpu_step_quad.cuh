@@ -414,6 +414,8 @@ __global__ void __launch_bounds__(NT, SLGPU_QUAD_MINBLOCKS) pt_step_quad_kernel(
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
       lg_att += (swap_type != 0);
+      if (p.round_flags) p.round_flags[(size_t)it * C + c] = (unsigned char)((acc ? 1 : 0) | (swap_type << 1));
+      if (it + 1 == p.n_rounds) p.lg_cur_energy[c] = mid_e; /* TableLogger energies_ (logging.cpp:43) */
       if (m.t == 0) {
         const double nn = (double)(r + 1);
         const double rnn = 1.0 / nn;

@@ -69,6 +69,10 @@ def lib():
     L.slo_n_models.argtypes = [C.c_void_p]
     L.slo_get_models.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
     L.slo_get_counters.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, _dp]
+    L.slo_get_logger.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.slo_window_rates.argtypes = [C.POINTER(C.c_int), C.c_uint32, _dp]
+    L.slo_format_table.restype = C.c_size_t
+    L.slo_format_table.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.slo_cold_rows.restype = C.c_uint64
     L.slo_cold_rows.argtypes = [C.c_void_p, C.c_uint32, _dp, C.c_uint64]
     L.slo_rhat.argtypes = [C.c_void_p, _dp]
@@ -195,6 +199,17 @@ class Sampler:
         lib().slo_get_counters(self.h, *[a.ctypes.data_as(_u64p) for a in arrs], _p(mine))
         return dict(length=arrs[0], accepts=arrs[1], swaps=arrs[2], swap_attempts=arrs[3], min_energy=mine)
 
+    def logger(self):
+        cur, ar, sr = np.empty(self.C), np.empty(self.C), np.empty(self.C)
+        lib().slo_get_logger(self.h, _p(cur), _p(ar), _p(sr))
+        return cur, ar, sr
+
+    def format_table(self):
+        n = lib().slo_format_table(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().slo_format_table(self.h, buf, n + 1)
+        return buf.value.decode()
+
     def cold_rows(self, stack):
         n = lib().slo_cold_rows(self.h, stack, None, 0)
         out = np.empty((n, self.d + 5))
@@ -285,6 +300,14 @@ def regression_update(xx, xy, w, count, min_cap, max_cap, logval, side, acc):
 def reduce_tree256(v):
     v = _f64(v)
     return lib().slo_reduce_tree256(_p(v), v.size, 1)
+
+
+def window_rates(flags):
+    """RegressionAdapter's logging window (adaptive.cpp:80-90): the rate after each flag."""
+    f = np.ascontiguousarray(flags, dtype=np.int32)
+    out = np.empty(f.size)
+    lib().slo_window_rates(f.ctypes.data_as(C.POINTER(C.c_int)), f.size, _p(out))
+    return out
 
 
 def csv_row(row, d):

@@ -548,7 +548,7 @@ struct slo_sampler {
   std::vector<double> ladder;      /* [T] */
   /* TableLogger counters + EPSR (logging.cpp:29-48) */
   std::vector<u64> lgLength, lgAccepts, lgSwaps, lgSwapAttempts;
-  std::vector<double> lgMinE;
+  std::vector<double> lgMinE, lgCurE; /* minEnergies_, energies_ (logging.cpp:22-23) */
   Epsr epsr;
   /* cold rows as CSVChainArrayWriter would receive them (chainarray.cpp:131-155) */
   std::vector<std::vector<double>> cold;
@@ -652,6 +652,7 @@ struct slo_sampler {
   void log_update(u32 id, const Row& s) {
     lgLength[id] += 1;
     lgMinE[id] = std::min(lgMinE[id], s.energy);
+    lgCurE[id] = s.energy; /* logging.cpp:43 */
     lgAccepts[id] += s.accepted;
     lgSwaps[id] += (s.swapType == 1);
     lgSwapAttempts[id] += (s.swapType != 0);
@@ -849,6 +850,7 @@ void slo_init_chains(slo_sampler* o) {
   o->lgSwaps.assign(C, 0);
   o->lgSwapAttempts.assign(C, 1);
   o->lgMinE.assign(C, std::numeric_limits<double>::infinity());
+  o->lgCurE.assign(C, 0.0);
   o->epsr.init(S, d);
   o->cold.assign(S, {});
   o->Psig.assign((size_t)C * 9, 0.0);
@@ -948,6 +950,73 @@ void slo_get_counters(const slo_sampler* o, uint64_t* length, uint64_t* accepts,
     if (swap_attempts) swap_attempts[c] = o->lgSwapAttempts[c];
     if (min_energy) min_energy[c] = o->lgMinE[c];
   }
+}
+
+void slo_get_logger(const slo_sampler* o, double* cur_energy, double* accept_rate, double* swap_rate) {
+  for (u32 c = 0; c < o->C; ++c) {
+    if (cur_energy) cur_energy[c] = o->lgCurE[c];
+    if (accept_rate) accept_rate[c] = o->sigAd.rates[c]; /* sigmaAdapter.rates(), sampler.cpp:198 */
+    if (swap_rate) swap_rate[c] = o->betaAd.rates[c];
+  }
+}
+
+/* the logging window of RegressionAdapter::update (adaptive.cpp:80-90) alone: rate after each of n flags */
+void slo_window_rates(const int* flags, uint32_t n, double* rates) {
+  Regression r;
+  r.init(1, 1, 0.5, 0.0, 1.0, false);
+  for (u32 i = 0; i < n; ++i) {
+    r.log_window(0, flags[i] != 0);
+    rates[i] = r.rates[0];
+  }
+}
+
+/* TableLogger::update's print branch, logging.cpp:52-87, on the current counters.  The reference streams into a
+ * stringstream with fill ' ', precision(5), showpoint | fixed and setw(4 / 9 / 10): by the num_put rules that is
+ * printf's "%4u", "%9lu" and "%#10.5f" ('#' is a no-op with a non-zero precision).  The convergence line goes to
+ * std::cout with default flags: "%g".  (printf rather than iostream: this library may be linked against a static
+ * libstdc++ whose stream locale is never initialised.) */
+size_t slo_format_table(const slo_sampler* o, char* out, size_t cap) {
+  std::string s = "\n\n  ID    Length    MinEngy   CurrEngy      Sigma     AcptRt  GlbAcptRt       Beta     SwapRt  GlbSwapRt\n";
+  s += "------------------------------------------------------------------------------------------------------\n";
+  char cell[64];
+  auto num = [&](double v) {
+    std::snprintf(cell, sizeof cell, "%#10.5f ", v);
+    s += cell;
+  };
+  for (u32 i = 0; i < o->C; i++) {
+    if (i % o->T == 0 && i != 0) s += '\n';
+    std::snprintf(cell, sizeof cell, "%4u %9lu ", i, (unsigned long)o->lgLength[i]);
+    s += cell;
+    num(o->lgMinE[i]);
+    num(o->lgCurE[i]);
+    num(o->sigma_[i]);
+    num(o->sigAd.rates[i]);
+    num(o->lgAccepts[i] / (double)o->lgLength[i]);
+    num(o->beta_[i]);
+    num(o->betaAd.rates[i]);
+    num(o->lgSwaps[i] / (double)o->lgSwapAttempts[i]);
+    s += '\n';
+  }
+  s += '\n'; /* std::cout << ss.str() << std::endl */
+  std::vector<double> rh(o->d);
+  o->epsr.rhat(rh.data());
+  double mean = 0.0;
+  bool conv = true;
+  for (u32 i = 0; i < o->d; ++i) {
+    mean += rh[i];
+    conv = conv && rh[i] < 1.1; /* diagnostics.hpp:35, diagnostics.cpp:73-76 */
+  }
+  mean /= (double)o->d;
+  std::snprintf(cell, sizeof cell, "Convergence test: %g (", mean);
+  s += cell;
+  s += conv ? "possibly converged" : "not converged";
+  s += ")\n";
+  if (out && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(out, s.data(), n);
+    out[n] = 0;
+  }
+  return s.size();
 }
 
 uint64_t slo_cold_rows(const slo_sampler* o, uint32_t stack, double* rows, uint64_t cap_rows) {

@@ -93,6 +93,11 @@ void slo_get_models(const slo_sampler*, int which /*0 sigma,1 beta*/, double* mu
 /* TableLogger counters (infer/logging.cpp:29-48), per chain */
 void slo_get_counters(const slo_sampler*, uint64_t* length, uint64_t* accepts, uint64_t* swaps,
                       uint64_t* swap_attempts, double* min_energy);
+/* TableLogger energies_ and the adapters' windowed rates_ (logging.cpp:43, adaptive.cpp:80-90), per chain */
+void slo_get_logger(const slo_sampler*, double* cur_energy, double* accept_rate, double* swap_rate);
+void slo_window_rates(const int* flags, uint32_t n, double* rates);
+/* the table + convergence line TableLogger::update prints (logging.cpp:52-87); returns the length */
+size_t slo_format_table(const slo_sampler*, char* out, size_t cap);
 /* cold-chain output rows in emission order: returns number of rows of that stack; rows[n][d+5].
  * Row 0 is the initial state (accepted=1). */
 uint64_t slo_cold_rows(const slo_sampler*, uint32_t stack, double* rows, uint64_t cap_rows);

@@ -25,6 +25,7 @@
 #include <limits>
 #include <sstream>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "json_min.hpp"
@@ -68,6 +69,7 @@ struct Settings {
   uint32_t adaptInterval = 0, maxRoundsPerLaunch = 64;
   uint64_t hostRingRounds = 0;
   bool overwrite = false;
+  bool windowRates = false;  // keep the adapters' windowed accept / swap rates (the AcptRt / SwapRt columns of the table logger)
   bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
 };
 
@@ -106,6 +108,8 @@ struct slgpu_engine {
   slgpu_step_params P{};
   double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
   void* d_payload = nullptr;
+  unsigned char* d_round_flags = nullptr;  // windowRates: [seg_rounds][C] per-round accept / swap flags of a launch
+  uint32_t *d_win_sig = nullptr, *d_win_beta = nullptr, *d_win_cnt = nullptr, *d_win_sum = nullptr;
   double *d_rp_z = nullptr, *d_rp_umh = nullptr, *d_rp_uswap = nullptr, *d_rp_xinit = nullptr;
   bool initialised = false, failed = false;
   uint64_t rounds_done = 0, launches = 0, rows_emitted = 0;
@@ -197,6 +201,7 @@ Settings parse_settings(const char* text) {
     if (g->find("maxRoundsPerLaunch")) s.maxRoundsPerLaunch = (uint32_t)need_uint(*g, "maxRoundsPerLaunch");
     if (g->find("hostRingRounds")) s.hostRingRounds = need_uint(*g, "hostRingRounds");
     if (g->find("overwrite")) s.overwrite = need(*g, "overwrite", slgpu_json::Value::Bool).b;
+    if (g->find("windowRates")) s.windowRates = need(*g, "windowRates", slgpu_json::Value::Bool).b;
     if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
     if (g->find("rng")) {
       const std::string& r = need(*g, "rng", slgpu_json::Value::String).str;
@@ -383,6 +388,13 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
     return fail(SLGPU_E_CUDA, std::string("launch_step: ") + cudaGetErrorString((cudaError_t)rc));
   }
   e->launches++;
+  if (e->d_round_flags) {
+    const uint32_t C = (uint32_t)e->C;
+    slgpu_tier::k_window_push<<<(C + 255) / 256, 256, 0, e->compute>>>(e->d_round_flags, n, C, e->cfg.nTemps, e->d_win_sig, e->d_win_beta,
+                                                                       e->d_win_cnt, e->d_win_sum);
+    CU_TRY(cudaGetLastError());
+    e->launches++;
+  }
   if (emit) {
     e->rows_emitted += n_rows;
     if (to_host) {
@@ -530,7 +542,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     TRY_ST(dev_alloc(e, &P.sh_count, C));
     TRY_ST(dev_alloc(e, &P.accepted, C)); TRY_ST(dev_alloc(e, &P.swap_type, C));
     TRY_ST(dev_alloc(e, &P.lg_accepts, C)); TRY_ST(dev_alloc(e, &P.lg_swaps, C)); TRY_ST(dev_alloc(e, &P.lg_swap_attempts, C));
-    TRY_ST(dev_alloc(e, &P.lg_min_energy, C));
+    TRY_ST(dev_alloc(e, &P.lg_min_energy, C)); TRY_ST(dev_alloc(e, &P.lg_cur_energy, C));
     TRY_ST(dev_alloc(e, &P.p_sig, 9 * C)); TRY_ST(dev_alloc(e, &P.p_beta, 9 * C));
     TRY_ST(dev_alloc(e, &P.ep_m, (size_t)d * S)); TRY_ST(dev_alloc(e, &P.ep_s, (size_t)d * S));
     TRY_ST(dev_alloc(e, &e->d_models, (size_t)2 * T * slgpu_tier::kModelStride));
@@ -545,7 +557,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
                   {"row_beta", P.row_beta, C * f8}, {"sigma", P.sigma, C * f8}, {"beta", P.beta, C * f8}, {"nscale", P.nscale, C * f8},
                   {"sh_count", P.sh_count, C * f8}, {"accepted", P.accepted, C * i4}, {"swap_type", P.swap_type, C * i4},
                   {"lg_accepts", P.lg_accepts, C * i4}, {"lg_swaps", P.lg_swaps, C * i4}, {"lg_swap_attempts", P.lg_swap_attempts, C * i4},
-                  {"lg_min_energy", P.lg_min_energy, C * f8}, {"p_sig", P.p_sig, 9 * C * f8}, {"p_beta", P.p_beta, 9 * C * f8},
+                  {"lg_min_energy", P.lg_min_energy, C * f8}, {"lg_cur_energy", P.lg_cur_energy, C * f8}, {"p_sig", P.p_sig, 9 * C * f8}, {"p_beta", P.p_beta, 9 * C * f8},
                   {"ep_m", P.ep_m, (size_t)d * S * f8}, {"ep_s", P.ep_s, (size_t)d * S * f8},
                   {"models", e->d_models, (size_t)2 * T * slgpu_tier::kModelStride * f8}, {"sig_w", e->d_sig_w, (size_t)3 * T * f8},
                   {"ladder", e->d_ladder, T * f8}};
@@ -557,6 +569,19 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     P.payload = e->d_payload;
     // sink
     e->seg_rounds = std::min(cfg.adaptInterval, cfg.maxRoundsPerLaunch);
+    if (cfg.windowRates) {
+      const size_t ringw = (size_t)slgpu_tier::kRingWords * C;
+      TRY_ST(dev_alloc(e, &e->d_round_flags, (size_t)e->seg_rounds * C));
+      TRY_ST(dev_alloc(e, &e->d_win_sig, ringw)); TRY_ST(dev_alloc(e, &e->d_win_beta, ringw));
+      TRY_ST(dev_alloc(e, &e->d_win_cnt, 2 * C)); TRY_ST(dev_alloc(e, &e->d_win_sum, 2 * C));
+      for (auto pr : {std::make_pair(e->d_win_sig, ringw), std::make_pair(e->d_win_beta, ringw), std::make_pair(e->d_win_cnt, 2 * C),
+                      std::make_pair(e->d_win_sum, 2 * C)})
+        CU_TRY(cudaMemset(pr.first, 0, pr.second * sizeof(uint32_t)));
+      P.round_flags = e->d_round_flags;
+      for (const StateBuf& b : {StateBuf{"win_sig", e->d_win_sig, ringw * 4}, StateBuf{"win_beta", e->d_win_beta, ringw * 4},
+                                StateBuf{"win_cnt", e->d_win_cnt, 2 * C * 4}, StateBuf{"win_sum", e->d_win_sum, 2 * C * 4}})
+        e->state.push_back(b);
+    }
     if (cfg.sink != SINK_NONE) {
       const size_t seg_doubles = (size_t)e->seg_rounds * S * e->row_w;
       const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;
@@ -1076,6 +1101,69 @@ slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_
   return SLGPU_OK;
 }
 
+
+// ---------------------------------------------------------------- table logger
+slgpu_status slgpu_get_logger(slgpu_engine* e, double* cur_energy, double* accept_rate, double* swap_rate) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  if ((accept_rate || swap_rate) && !e->d_win_cnt)
+    return fail(SLGPU_E_STATE, "the windowed rates need \"gpu\": {\"windowRates\": true}");
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  const size_t C = e->C;
+  if (cur_energy) CU_TRY(cudaMemcpy(cur_energy, e->P.lg_cur_energy, C * sizeof(double), cudaMemcpyDeviceToHost));
+  if (accept_rate || swap_rate) {
+    std::vector<uint32_t> cnt, sum;
+    if ((st = fetch(cnt, e->d_win_cnt, 2 * C)) != SLGPU_OK || (st = fetch(sum, e->d_win_sum, 2 * C)) != SLGPU_OK) return st;
+    // rates_ = window_sum / size-before-pop (adaptive.cpp:83-90); 0 until the first update (adaptive.cpp:38)
+    auto rate = [&](size_t i) { return cnt[i] ? (double)sum[i] / (double)std::min<uint32_t>(cnt[i], slgpu_tier::kWindow) : 0.0; };
+    for (size_t c = 0; c < C; ++c) {
+      if (accept_rate) accept_rate[c] = rate(c);
+      if (swap_rate) swap_rate[c] = rate(C + c);
+    }
+  }
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_format_table(slgpu_engine* e, char* out, size_t cap, size_t* needed) {
+  slgpu_status st = check_ready(e, true);
+  if (st != SLGPU_OK) return st;
+  const size_t C = e->C;
+  const uint32_t S = e->cfg.nStacks, T = e->cfg.nTemps, d = e->cfg.nDims;
+  std::vector<uint64_t> len(C), acc(C), sw(C), att(C);
+  std::vector<double> minE(C), curE(C), sigma(C), beta(C), ar(C), sr(C), rhat(d);
+  if ((st = slgpu_get_counters(e, len.data(), acc.data(), sw.data(), att.data(), minE.data())) != SLGPU_OK) return st;
+  if ((st = slgpu_get_logger(e, curE.data(), ar.data(), sr.data())) != SLGPU_OK) return st;
+  if ((st = slgpu_get_sigma_beta(e, sigma.data(), beta.data())) != SLGPU_OK) return st;
+  if ((st = slgpu_rhat(e, rhat.data())) != SLGPU_OK) return st;
+  // TableLogger::update, logging.cpp:52-87: fixed, precision 5, widths 4 / 9 / 10
+  std::string s = "\n\n  ID    Length    MinEngy   CurrEngy      Sigma     AcptRt  GlbAcptRt       Beta     SwapRt  GlbSwapRt\n";
+  s += std::string(102, '-') + "\n";
+  char line[256];
+  for (size_t i = 0; i < C; ++i) {
+    if (i % T == 0 && i != 0) s += '\n';
+    std::snprintf(line, sizeof line, "%4zu %9llu %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f \n", i, (unsigned long long)len[i],
+                  minE[i], curE[i], sigma[i], ar[i], (double)acc[i] / (double)len[i], beta[i], sr[i], (double)sw[i] / (double)att[i]);
+    s += line;
+  }
+  s += '\n';  // std::endl after the table
+  double mean = 0.0;
+  bool converged = true;
+  for (uint32_t i = 0; i < d; ++i) {
+    mean += rhat[i];
+    converged = converged && rhat[i] < 1.1;  // EPSRDiagnostic threshold, diagnostics.hpp:35
+  }
+  mean /= (double)d;
+  std::snprintf(line, sizeof line, "Convergence test: %g (%s)\n", mean, converged ? "possibly converged" : "not converged");
+  s += line;
+  (void)S;
+  if (needed) *needed = s.size() + 1;
+  if (out && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(out, s.data(), n);
+    out[n] = 0;
+  }
+  return SLGPU_OK;
+}
 
 // ---------------------------------------------------------------- checkpoint / resume
 // The reference declares ChainArray::recoverFromDisk (src/infer/chainarray.hpp:158-162) but never defines it; a

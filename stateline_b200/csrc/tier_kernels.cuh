@@ -186,4 +186,39 @@ __global__ void k_tier_solve(const double* sums, uint32_t T, double* models, dou
   if (i == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
 }
 
+// The acceptance windows of RegressionAdapter::update (adaptive.cpp:80-90), logging only: every chain keeps the last
+// accept flags of its sigma adapter (one per round) and of its beta adapter (one per swap attempt of the pair
+// (chain, chain+1)).  The reference's deque holds 999 flags once it has seen 1000 (it pushes, then pops when the size
+// reaches n_window_ = 1000) and divides by the size before the pop: rate = sum(last 999) / 1000, and sum(all) / k
+// while k < 1000.  Here: a 1024-bit ring per chain and adapter, ring[word][chain], updated after every launch from
+// the per-round flags the step kernel logged.  win[0..1] = rings (sigma, beta), cnt / sum = [2][C].
+constexpr uint32_t kWindow = 1000;  // adaptive.cpp:29
+constexpr uint32_t kRingWords = 32;
+
+__device__ inline void window_push(uint32_t* ring, size_t C, size_t c, uint32_t& k, uint32_t& sum, uint32_t bit) {
+  k += 1;
+  const uint32_t pos = k & 1023u;
+  uint32_t* w = ring + (size_t)(pos >> 5) * C + c;
+  *w = (*w & ~(1u << (pos & 31u))) | (bit << (pos & 31u));
+  sum += bit;
+  if (k >= kWindow) {
+    const uint32_t old = (k - (kWindow - 1)) & 1023u;
+    sum -= (ring[(size_t)(old >> 5) * C + c] >> (old & 31u)) & 1u;
+  }
+}
+
+__global__ void k_window_push(const unsigned char* flags, uint32_t n_rounds, uint32_t C, uint32_t T, uint32_t* ring_sig,
+                              uint32_t* ring_beta, uint32_t* cnt, uint32_t* sum) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  uint32_t ks = cnt[c], kb = cnt[C + c], ss = sum[c], sb = sum[C + c];
+  for (uint32_t r = 0; r < n_rounds; ++r) {
+    const uint32_t f = flags[(size_t)r * C + c];
+    window_push(ring_sig, C, c, ks, ss, f & 1u);
+    const uint32_t st = f >> 1;  // swapType: 0 none, 1 accepted, 2 rejected
+    if (st != 0 && c % T != T - 1) window_push(ring_beta, C, c, kb, sb, st == 1u ? 1u : 0u);
+  }
+  cnt[c] = ks; cnt[C + c] = kb; sum[c] = ss; sum[C + c] = sb;
+}
+
 }  // namespace slgpu_tier

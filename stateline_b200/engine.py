@@ -29,7 +29,7 @@ SYMBOLS = [
     "slgpu_get_sigma_beta", "slgpu_get_shaper", "slgpu_get_models", "slgpu_get_ladder",
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
-    "slgpu_save_state", "slgpu_load_state",
+    "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
 ]
 
 BUILTIN_ENTRIES = {
@@ -99,6 +99,8 @@ def lib():
     L.slgpu_format_row.argtypes = [_dp, C.c_uint32, C.c_char_p, C.c_size_t]
     L.slgpu_format_row.restype = C.c_size_t
     L.slgpu_measure_fp64_peak.argtypes = [C.c_int, _dp]
+    L.slgpu_get_logger.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.slgpu_format_table.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, _szp]
     L.slgpu_save_state.argtypes = [C.c_void_p, C.c_char_p]
     L.slgpu_load_state.argtypes = [C.c_void_p, C.c_char_p]
     _lib = L
@@ -207,6 +209,23 @@ class Engine:
 
     def run(self):
         _check(lib().slgpu_run(self.h))
+
+    def logger(self, rates=True):
+        """TableLogger columns per chain: (cur_energy, accept_rate, swap_rate); the windowed rates need
+        "gpu": {"windowRates": true} (pass rates=False to get the energies alone)."""
+        cur = np.empty(self.C)
+        ar = np.empty(self.C) if rates else None
+        sr = np.empty(self.C) if rates else None
+        _check(lib().slgpu_get_logger(self.h, _p(cur), _p(ar) if rates else None, _p(sr) if rates else None))
+        return cur, ar, sr
+
+    def format_table(self):
+        """The table TableLogger::update prints (src/infer/logging.cpp:52-87) plus its convergence line."""
+        need = C.c_size_t()
+        _check(lib().slgpu_format_table(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().slgpu_format_table(self.h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
 
     def save_state(self, path):
         """Checkpoint every chain, the tier models and the round counter (slgpu_save_state)."""

@@ -312,3 +312,60 @@ def test_csv_resume_appends(tmp_path):
         a = open(tmp_path / "whole" / ("%d.csv" % s)).read()
         b = open(tmp_path / "parts" / ("%d.csv" % s)).read()
         assert a == b and a.count("\n") == 51
+
+
+@pytest.mark.parametrize("name,S,rounds,swap_interval", [("config1", 2, 30, None), ("config2", 8, 2300, 2), ("config4", 2, 45, 5)])
+def test_table_logger_matches_oracle(name, S, rounds, swap_interval):
+    """TableLogger parity (src/infer/logging.cpp:35-87): energies_, the adapters' windowed rates (adaptive.cpp:80-90;
+    2300 rounds with swapInterval 2 wrap both 1000-entry windows) and the printed table, character for character."""
+    w = configs.workload(name, S=S)
+    if swap_interval:
+        w["swapInterval"] = swap_interval
+    with engine_for(w, seed=9, sink="none", windowRates=True) as eng:
+        eng.init_chains()
+        first = eng.format_table()
+        eng.step_rounds(rounds)
+        got_log, got_table = eng.logger(), eng.format_table()
+    orc = oracle_for(w, seed=9)
+    orc.init_chains()
+    assert first == orc.format_table()
+    orc.run_rounds(rounds)
+    for a, b in zip(got_log, orc.logger()):
+        assert np.array_equal(a, b)
+    assert got_table == orc.format_table()
+    with engine_for(w, seed=9, sink="none") as eng:
+        eng.init_chains()
+        eng.step_rounds(3)
+        assert np.array_equal(eng.logger(rates=False)[0], oracle_cur3(w))
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.format_table()  # the windowed-rate columns were not asked for
+        assert ei.value.status == engine.E_STATE
+
+
+def oracle_cur3(w):
+    orc = oracle_for(w, seed=9)
+    orc.init_chains()
+    orc.run_rounds(3)
+    return orc.logger()[0]
+
+
+def test_checkpoint_keeps_the_rate_windows(tmp_path):
+    w = configs.workload("config2", S=4)
+    w["swapInterval"] = 3
+    with engine_for(w, seed=2, sink="none", windowRates=True) as eng:
+        eng.init_chains()
+        eng.step_rounds(1300)
+        want = eng.format_table()
+    ck = tmp_path / "w.slgpu"
+    with engine_for(w, seed=2, sink="none", windowRates=True) as eng:
+        eng.init_chains()
+        eng.step_rounds(1100)
+        eng.save_state(ck)
+    with engine_for(w, seed=2, sink="none", windowRates=True) as eng:
+        eng.load_state(ck)
+        eng.step_rounds(200)
+        assert eng.format_table() == want
+    with engine_for(w, seed=2, sink="none") as eng:
+        with pytest.raises(sb.SlgpuError) as ei:
+            eng.load_state(ck)  # a checkpoint with windows does not fit an engine without them
+        assert ei.value.status == engine.E_CONFIG

@@ -199,3 +199,40 @@ def test_posterior_moments_config1():
     assert abs(x[:, 0].std() - sd) < 0.03 and abs(x[:, 2].std() - sd) < 0.03
     assert abs(x[:, 1].mean() - sd * np.sqrt(2.0 / np.pi)) < 0.03  # half-normal mean
     assert x[:, 1].min() >= 0.0 and x[:, 3].max() <= 2.0
+
+
+def test_logging_window_quirk():
+    """RegressionAdapter's logging window (adaptive.cpp:80-90) pushes, then pops once the deque holds n_window_ = 1000
+    flags, and divides by the size before the pop: the rate is sum(all)/k for k < 1000 and sum(last 999)/1000 after."""
+    rng = np.random.default_rng(5)
+    f = (rng.random(2600) < 0.3).astype(np.int32)
+    got = O.window_rates(f)
+    want = np.empty(f.size)
+    for i in range(f.size):
+        k = i + 1
+        want[i] = f[:k].sum() / k if k < 1000 else f[k - 999:k].sum() / 1000.0
+    assert np.array_equal(got, want)
+
+
+def test_table_logger_format():
+    """The text of TableLogger::update (logging.cpp:52-87): header literal, the dashed rule, one line per chain
+    ("%4u %9lu" then eight "%10.5f " cells), a blank line between stacks, the convergence line."""
+    s = O.Sampler(S=2, T=5, J=3, swap_interval=10, opt_accept=0.234, opt_swap=0.3874, mn=[-10, 0, -10, -10],
+                  mx=[10, 10, 10, 2], target=O.TARGET_DEMO_GAUSS, schedule=O.SCHED_BATCHED, seed=4)
+    s.init_chains()
+    before = s.format_table().split("\n")
+    assert before[4].split() == ["0", "1", "inf", "0.00000", "1.00000", "0.00000", "1.00000", "1.00000", "0.00000", "0.00000"]
+    s.run_rounds(30)
+    lines = s.format_table().split("\n")
+    assert lines[0] == "" and lines[1] == ""
+    assert lines[2] == "  ID    Length    MinEngy   CurrEngy      Sigma     AcptRt  GlbAcptRt       Beta     SwapRt  GlbSwapRt"
+    assert lines[3] == "-" * 102
+    body = lines[4:4 + 11]
+    assert body[5] == "" and all(len(b) == 4 + 1 + 9 + 1 + 8 * 11 + 0 for i, b in enumerate(body) if i != 5)
+    c, (cur, ar, sr), (sig, beta) = s.counters(), s.logger(), s.sigma_beta()
+    want = "%4d %9d %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f %10.5f " % (
+        7, c["length"][7], c["min_energy"][7], cur[7], sig[7], ar[7], c["accepts"][7] / c["length"][7], beta[7], sr[7],
+        c["swaps"][7] / c["swap_attempts"][7])
+    assert body[8] == want
+    assert lines[15] == "" and lines[16] == "Convergence test: %g (not converged)" % s.rhat().mean()
+    assert lines[17:] == [""]
