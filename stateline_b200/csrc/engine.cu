@@ -17,6 +17,10 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <charconv>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -70,6 +74,7 @@ struct Settings {
   uint64_t hostRingRounds = 0;
   bool overwrite = false;
   bool windowRates = false;  // keep the adapters' windowed accept / swap rates (the AcptRt / SwapRt columns of the table logger)
+  uint32_t csvThreads = 0;  // csv sink: formatter threads (0 = one per host core, at most 16)
   bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
 };
 
@@ -89,6 +94,20 @@ struct StateBuf {
   const char* name;
   void* dev;
   size_t bytes;
+};
+
+
+// Formatter pool of the csv sink.  Rows arrive round-major (row r belongs to stack r % S); worker w owns the stacks
+// s with s % n == w -- their text buffers and their files -- so a batch needs no locking beyond the fork / join.
+struct CsvPool {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable go, done;
+  uint64_t generation = 0;
+  uint32_t running = 0;
+  bool stop = false, flush = false, io_error = false;
+  uint64_t r0 = 0, r1 = 0;
+  std::vector<size_t> buffered;  // bytes held per worker
 };
 
 }  // namespace
@@ -125,7 +144,7 @@ struct slgpu_engine {
   std::vector<cudaEvent_t> ev_pool;
   // csv sink
   std::vector<std::string> csv_buf;
-  size_t csv_buffered = 0;
+  CsvPool csv;
 };
 
 namespace {
@@ -202,6 +221,7 @@ Settings parse_settings(const char* text) {
     if (g->find("hostRingRounds")) s.hostRingRounds = need_uint(*g, "hostRingRounds");
     if (g->find("overwrite")) s.overwrite = need(*g, "overwrite", slgpu_json::Value::Bool).b;
     if (g->find("windowRates")) s.windowRates = need(*g, "windowRates", slgpu_json::Value::Bool).b;
+    if (g->find("csvThreads")) s.csvThreads = (uint32_t)need_uint(*g, "csvThreads");
     if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
     if (g->find("rng")) {
       const std::string& r = need(*g, "rng", slgpu_json::Value::String).str;
@@ -269,56 +289,131 @@ void poll_landed(slgpu_engine* e, bool block) {
     e->rows_consumed = e->rows_landed - e->ring_rows;
 }
 
-size_t format_row(const double* row, uint32_t d, char* out, size_t cap) {
-  // operator<<(ostream&, State), src/db/db.cpp:18-25: default ostream formatting == "%g"
-  std::string s;
-  char buf[64];
-  for (uint32_t i = 0; i < d; ++i) {
-    std::snprintf(buf, sizeof buf, "%g,", row[i]);
-    s += buf;
+// One value as operator<<(ostream&, double) prints it with default flags (precision 6, general): printf's "%g".
+// std::to_chars(general, 6) is specified to produce exactly that text and is several times faster than snprintf.
+inline char* put_g(char* p, double v) {
+  if (!std::isfinite(v)) return p + std::snprintf(p, 16, "%g", v);
+  return std::to_chars(p, p + 32, v, std::chars_format::general, 6).ptr;
+}
+
+// operator<<(ostream&, State), src/db/db.cpp:18-25; buf must hold 32 * (d + 5) bytes.  Returns the length.
+inline size_t format_row_into(const double* row, uint32_t d, char* buf) {
+  char* p = buf;
+  for (uint32_t i = 0; i < d + 3; ++i) {
+    p = put_g(p, row[i]);
+    *p++ = ',';
   }
-  std::snprintf(buf, sizeof buf, "%g,%g,%g,%d,%d", row[d], row[d + 1], row[d + 2], (int)row[d + 3], (int)row[d + 4]);
-  s += buf;
+  p = std::to_chars(p, p + 16, (int)row[d + 3]).ptr;
+  *p++ = ',';
+  p = std::to_chars(p, p + 16, (int)row[d + 4]).ptr;
+  return (size_t)(p - buf);
+}
+
+size_t format_row(const double* row, uint32_t d, char* out, size_t cap) {
+  std::vector<char> buf((size_t)32 * (d + SLGPU_ROW_EXTRA));
+  const size_t len = format_row_into(row, d, buf.data());
   if (out && cap) {
-    const size_t n = std::min(cap - 1, s.size());
-    std::memcpy(out, s.data(), n);
+    const size_t n = std::min(cap - 1, len);
+    std::memcpy(out, buf.data(), n);
     out[n] = 0;
   }
-  return s.size();
+  return len;
 }
 
 std::string csv_path(const slgpu_engine* e, uint32_t local_stack) {
   return e->cfg.outputPath + "/" + std::to_string(e->cfg.stackOffset + local_stack) + ".csv";
 }
 
-slgpu_status csv_flush_files(slgpu_engine* e) {
-  for (uint32_t s = 0; s < e->cfg.nStacks; ++s) {
-    if (e->csv_buf[s].empty()) continue;
-    std::ofstream f(csv_path(e, s), std::ios::app | std::ios::binary);
-    if (!f.good()) return fail(SLGPU_E_IO, "cannot append to " + csv_path(e, s));
-    f.write(e->csv_buf[s].data(), (std::streamsize)e->csv_buf[s].size());
-    e->csv_buf[s].clear();
+// worker w of n: format rows [r0, r1) of its stacks, then (flush) append its buffers to <outputPath>/<stack>.csv
+void csv_work(slgpu_engine* e, uint32_t w, uint32_t n, uint64_t r0, uint64_t r1, bool flush) {
+  const uint32_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  char line[32 * (SLGPU_MAX_DIMS + SLGPU_ROW_EXTRA) + 1];
+  size_t held = e->csv.buffered[w];
+  for (uint32_t s = w; s < S; s += n) {
+    std::string& b = e->csv_buf[s];
+    uint64_t r = r0 + (s + S - (uint32_t)(r0 % S)) % S;  // first row >= r0 of stack s
+    for (; r < r1; r += S) {
+      const double* row = e->ring + (size_t)(r % e->ring_rows) * e->row_w;
+      size_t len = format_row_into(row, d, line);
+      line[len++] = '\n';
+      b.append(line, len);
+      held += len;
+    }
+    if (flush && !b.empty()) {
+      FILE* f = std::fopen(csv_path(e, s).c_str(), "ab");
+      const bool ok = f && std::fwrite(b.data(), 1, b.size(), f) == b.size();
+      if (f) std::fclose(f);
+      if (!ok) {
+        std::lock_guard<std::mutex> lk(e->csv.m);
+        e->csv.io_error = true;
+      }
+      b.clear();
+    }
   }
-  e->csv_buffered = 0;
-  return SLGPU_OK;
+  e->csv.buffered[w] = flush ? 0 : held;
 }
 
-// format every landed row into the per-stack buffers (one <outputPath>/<stack>.csv per stack, db.cpp:27-35)
+void csv_worker_main(slgpu_engine* e, uint32_t w, uint32_t n) {
+  CsvPool& cp = e->csv;
+  uint64_t seen = 0;
+  for (;;) {
+    uint64_t r0, r1;
+    bool flush;
+    {
+      std::unique_lock<std::mutex> lk(cp.m);
+      cp.go.wait(lk, [&] { return cp.stop || cp.generation != seen; });
+      if (cp.stop) return;
+      seen = cp.generation;
+      r0 = cp.r0; r1 = cp.r1; flush = cp.flush;
+    }
+    csv_work(e, w, n, r0, r1, flush);
+    {
+      std::lock_guard<std::mutex> lk(cp.m);
+      if (--cp.running == 0) cp.done.notify_one();
+    }
+  }
+}
+
+void csv_pool_start(slgpu_engine* e) {
+  uint32_t n = e->cfg.csvThreads ? e->cfg.csvThreads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  n = std::max(1u, std::min(n, e->cfg.nStacks));
+  e->csv.buffered.assign(n, 0);
+  if (n == 1) return;  // the caller's thread does the work
+  for (uint32_t w = 0; w < n; ++w) e->csv.threads.emplace_back(csv_worker_main, e, w, n);
+}
+
+void csv_pool_stop(slgpu_engine* e) {
+  {
+    std::lock_guard<std::mutex> lk(e->csv.m);
+    e->csv.stop = true;
+  }
+  e->csv.go.notify_all();
+  for (auto& t : e->csv.threads) t.join();
+  e->csv.threads.clear();
+}
+
+// format every landed row into the per-stack buffers (one <outputPath>/<stack>.csv per stack, db.cpp:27-35);
+// buffers go to the files when they hold 64 MiB together, and at the end (finalise)
 slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
   poll_landed(e, block);
-  char line[64 * (SLGPU_MAX_DIMS + 8)];
-  const uint32_t S = e->cfg.nStacks, d = e->cfg.nDims;
-  while (e->rows_consumed < e->rows_landed) {
-    const uint64_t r = e->rows_consumed;
-    const double* row = e->ring + (size_t)(r % e->ring_rows) * e->row_w;
-    const size_t n = format_row(row, d, line, sizeof line);
-    std::string& b = e->csv_buf[(size_t)(r % S)];
-    b.append(line, n);
-    b.push_back('\n');
-    e->csv_buffered += n + 1;
-    e->rows_consumed++;
+  CsvPool& cp = e->csv;
+  size_t held = 0;
+  for (size_t b : cp.buffered) held += b;
+  const uint64_t r0 = e->rows_consumed, r1 = e->rows_landed;
+  const bool flush = finalise || held + (r1 - r0) * 12 * e->row_w > (64u << 20);
+  if (r0 == r1 && !(flush && held)) return SLGPU_OK;
+  if (cp.threads.empty()) {
+    csv_work(e, 0, 1, r0, r1, flush);
+  } else {
+    std::unique_lock<std::mutex> lk(cp.m);
+    cp.r0 = r0; cp.r1 = r1; cp.flush = flush;
+    cp.running = (uint32_t)cp.threads.size();
+    cp.generation++;
+    cp.go.notify_all();
+    cp.done.wait(lk, [&] { return cp.running == 0; });
   }
-  if (finalise || e->csv_buffered > (64u << 20)) return csv_flush_files(e);
+  e->rows_consumed = r1;
+  if (cp.io_error) return fail(SLGPU_E_IO, "cannot append to the csv files under " + e->cfg.outputPath);
   return SLGPU_OK;
 }
 
@@ -602,6 +697,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
       // CSVChainArrayWriter ctor, db.cpp:27-35: one file per stack, truncated on open
       mkdir(cfg.outputPath.c_str(), 0777);
       e->csv_buf.assign(S, std::string());
+      csv_pool_start(e);
       for (uint32_t s = 0; s < S; ++s) {
         std::ofstream f(csv_path(e, s), cfg.append ? std::ios::app : std::ios::trunc);
         if (!f.good()) return fail(SLGPU_E_IO, "cannot create " + csv_path(e, s));
@@ -629,6 +725,10 @@ void slgpu_destroy(slgpu_engine* e) {
   cudaSetDevice(e->cfg.device);
   if (e->compute) cudaStreamSynchronize(e->compute);
   if (e->drain) cudaStreamSynchronize(e->drain);
+  if (e->cfg.sink == SINK_CSV) {
+    if (e->initialised && !e->failed && e->ring) csv_pump(e, true, true);
+    csv_pool_stop(e);
+  }
   for (void* p : e->allocs) cudaFree(p);
   for (auto& p : {e->d_rp_z, e->d_rp_umh, e->d_rp_uswap, e->d_rp_xinit})
     if (p) cudaFree(p);
@@ -734,7 +834,9 @@ slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds) {
 slgpu_status slgpu_sync(slgpu_engine* e) {
   slgpu_status st = check_ready(e, false);
   if (st != SLGPU_OK) return st;
-  return sync_all(e);
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  if (e->cfg.sink == SINK_CSV && e->initialised) return csv_pump(e, true, true);  // every landed row is in its file
+  return SLGPU_OK;
 }
 
 slgpu_status slgpu_run(slgpu_engine* e) {

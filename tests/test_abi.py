@@ -1,6 +1,7 @@
 """CPU tests of the drop-in boundary: libslgpu.so loads, exports every symbol include/slgpu.h declares,
 and the host logic in front of the device (config reader, plugin loading, error convention) behaves.
 No compute call is made: there is no GPU here and the engine has no CPU fallback."""
+import numpy as np
 import ctypes as C
 import json
 import os
@@ -122,3 +123,22 @@ def test_format_row_matches_reference_stream_format():
     assert sb.format_row(row, 3) == "0.25,-1.23457e+06,1e-07,2.5,0.123457,1,1,2"
     from oracle import oracle as O
     assert sb.format_row(row, 3) == O.csv_row(row, 3)
+
+
+def test_format_row_is_printf_g_for_every_kind_of_value():
+    """The csv sink formats with std::to_chars(general, 6); the reference streams doubles with default flags,
+    i.e. printf's %g.  Same text on magnitudes across the fixed / scientific switch, rounding ties at the sixth
+    digit, subnormals, zeros and non-finite values."""
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([
+        rng.standard_normal(4000) * 10.0 ** rng.integers(-12, 13, 4000),
+        rng.integers(-2_000_000, 2_000_000, 2000).astype(np.float64) / 1000.0,
+        np.array([0.0, -0.0, 1e-5, 9.9999949e-5, 9.9999951e-5, 1e-4, 99999.95, 999999.5, 999999.4, 1e6, 123456.5, 0.1234565,
+                  2.5e-310, 1.7976931348623157e308, 5e-324, np.inf, -np.inf, 100000.0, 1234565.0, 0.5, 1.0, -1.0, 1e21, 1e-21]),
+    ])
+    d = 20
+    vals = vals[: (vals.size // (d + 3)) * (d + 3)].reshape(-1, d + 3)
+    for i, v in enumerate(vals):
+        row = np.concatenate([v, [i % 2, i % 3]])
+        want = ",".join("%g" % x for x in v) + ",%d,%d" % (i % 2, i % 3)
+        assert sb.format_row(row, d) == want

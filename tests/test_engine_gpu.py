@@ -369,3 +369,26 @@ def test_checkpoint_keeps_the_rate_windows(tmp_path):
         with pytest.raises(sb.SlgpuError) as ei:
             eng.load_state(ck)  # a checkpoint with windows does not fit an engine without them
         assert ei.value.status == engine.E_CONFIG
+
+
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_csv_formatter_pool(tmp_path, threads):
+    """The csv sink's formatter threads own disjoint stacks; whatever their number, every <stack>.csv holds that
+    stack's rows in order, as the oracle formats them (a 7-round ring forces many pump / back-pressure cycles)."""
+    w = configs.workload("config2", S=37)
+    cfg = configs.engine_config(w, sink="csv", seed=6, csvThreads=threads, hostRingRounds=7)
+    cfg["outputPath"] = str(tmp_path / "out")
+    with Engine(cfg, plugin=w["plugin"]) as eng:
+        eng.init_chains()
+        for n in (1, 5, 33, 20):
+            eng.step_rounds(n)
+        eng.sync()  # flushes
+        orc = oracle_for(w, seed=6)
+        orc.init_chains()
+        orc.run_rounds(59)
+        for s in (0, 1, 17, 36):
+            lines = open(os.path.join(cfg["outputPath"], "%d.csv" % s)).read().splitlines()
+            assert lines == [O.csv_row(r, w["d"]) for r in orc.cold_rows(s)]
+        eng.step_rounds(4)
+    # destroy flushed the last four rounds
+    assert open(os.path.join(cfg["outputPath"], "36.csv")).read().count("\n") == 64
