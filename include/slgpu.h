@@ -151,7 +151,8 @@ slgpu_status slgpu_format_table(slgpu_engine* e, char* out, size_t cap, size_t* 
  * created from the same configuration and plugin (SLGPU_E_CONFIG otherwise; SLGPU_E_IO for a missing, foreign or
  * truncated file, which leaves the engine untouched); it replaces slgpu_init_chains.  The random streams are
  * addressed by round index, so a resumed run continues bit for bit.  Rows emitted before the checkpoint are not
- * emitted again; with sink "csv" create the resuming engine with "gpu": {"append": true}. */
+ * emitted again; with sink "csv" create the resuming engine with "gpu": {"append": true}.  The logging windows of
+ * "gpu": {"windowRates": true} are optional on both sides: a checkpoint without them resumes with empty windows. */
 slgpu_status slgpu_save_state(slgpu_engine* e, const char* path);
 slgpu_status slgpu_load_state(slgpu_engine* e, const char* path);
 

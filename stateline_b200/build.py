@@ -13,6 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 
 ENGINE_SO = os.path.join(PKG, "libslgpu.so")
 TARGETS_SO = os.path.join(PKG, "libslgpu_targets.so")
+CLI_EXE = os.path.join(PKG, "stateline-gpu")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: products and sums round separately unless fma() is written out (bit parity with the oracle)
@@ -90,8 +91,22 @@ def build_targets(force=False, verbose=False):
     return build_plugin(os.path.join(PKG, "plugins", "builtin_targets.cu"), TARGETS_SO, force, verbose)
 
 
+def build_cli(force=False, verbose=False, out=CLI_EXE):
+    """stateline-gpu: the `stateline -c config.json` server binary for the GPU path (plain C++ over the C-ABI)."""
+    build_engine(force, verbose)
+    src = os.path.join(PKG, "cli", "stateline_gpu.cpp")
+    cxx = shutil.which("g++") or "g++"
+    flags = ["-std=c++17", "-O2", "-I" + INCLUDE, "-I" + CSRC]
+    digest = _digest([src, os.path.join(INCLUDE, "slgpu.h"), os.path.join(CSRC, "json_min.hpp")], flags)
+    if force and os.path.exists(out + ".srchash"):
+        os.remove(out + ".srchash")
+    if _stale(out, digest):
+        _compile([cxx] + flags + [src, "-L" + PKG, "-lslgpu", "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN", "-o", out], out, digest, verbose)
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return build_engine(force, verbose), build_targets(force, verbose)
+    return build_engine(force, verbose), build_targets(force, verbose), build_cli(force, verbose)
 
 
 if __name__ == "__main__":

@@ -1365,20 +1365,33 @@ slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
     return fail(SLGPU_E_IO, std::string(path) + " is not a slgpu checkpoint");
   CkHeader want = ck_header(e);
   want.rounds_done = h.rounds_done;
+  want.n_sections = h.n_sections;  // the rate windows are optional on either side (see below)
   if (std::memcmp(&h, &want, sizeof h) != 0)
     return fail(SLGPU_E_CONFIG, std::string(path) + " was written by a run with a different configuration (shape, bounds, seed, rates or plugin)");
   // read everything before touching the device: a truncated file must leave the engine as it was
-  std::vector<std::vector<char>> data(e->state.size());
-  for (size_t i = 0; i < e->state.size(); ++i) {
-    const StateBuf& b = e->state[i];
+  std::vector<std::pair<std::string, std::vector<char>>> file_secs(h.n_sections);
+  for (auto& fs : file_secs) {
     CkSection sec;
-    if (std::fread(&sec, sizeof sec, 1, fc.f) != 1 || std::strncmp(sec.name, b.name, sizeof sec.name) != 0 || sec.bytes != b.bytes)
-      return fail(SLGPU_E_IO, std::string(path) + ": section " + b.name + " is missing or has the wrong size");
-    data[i].resize(b.bytes);
-    if (b.bytes && std::fread(data[i].data(), b.bytes, 1, fc.f) != 1) return fail(SLGPU_E_IO, std::string(path) + " is truncated");
+    if (std::fread(&sec, sizeof sec, 1, fc.f) != 1 || sec.bytes > ((uint64_t)1 << 40)) return fail(SLGPU_E_IO, std::string(path) + " is truncated");
+    sec.name[sizeof sec.name - 1] = 0;
+    fs.first = sec.name;
+    fs.second.resize(sec.bytes);
+    if (sec.bytes && std::fread(fs.second.data(), sec.bytes, 1, fc.f) != 1) return fail(SLGPU_E_IO, std::string(path) + " is truncated");
   }
-  for (size_t i = 0; i < e->state.size(); ++i)
-    CU_TRY(cudaMemcpy(e->state[i].dev, data[i].data(), e->state[i].bytes, cudaMemcpyHostToDevice));
+  // The logging windows ("win_*", gpu.windowRates) do not feed back into the chains: a checkpoint without them
+  // resumes with empty windows, one with them loads into an engine that does not keep any.
+  auto optional = [](const std::string& name) { return name.rfind("win_", 0) == 0; };
+  std::vector<const std::vector<char>*> src(e->state.size(), nullptr);
+  for (size_t i = 0; i < e->state.size(); ++i) {
+    for (const auto& fs : file_secs)
+      if (fs.first == e->state[i].name) src[i] = &fs.second;
+    if (src[i] ? src[i]->size() != e->state[i].bytes : !optional(e->state[i].name))
+      return fail(SLGPU_E_IO, std::string(path) + ": section " + e->state[i].name + " is missing or has the wrong size");
+  }
+  for (size_t i = 0; i < e->state.size(); ++i) {
+    if (src[i]) CU_TRY(cudaMemcpy(e->state[i].dev, src[i]->data(), e->state[i].bytes, cudaMemcpyHostToDevice));
+    else CU_TRY(cudaMemset(e->state[i].dev, 0, e->state[i].bytes));
+  }
   e->rounds_done = h.rounds_done;
   e->initialised = true;
   return SLGPU_OK;

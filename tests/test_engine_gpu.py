@@ -188,20 +188,41 @@ def test_user_plugin_and_cpp_host(tmp_path):
     r = np.linalg.norm(rows[:, :3], axis=1)
     assert r.max() <= 2.0 and np.all(np.isfinite(rows[:, 3]))           # never left the ball: +inf proposals always rejected
     assert abs(np.median(r[8 * 200:]) - 1.5) < 0.2                        # and sits on the ring
-    # C++ host example against the built-in demo target, csv sink
-    exe = str(tmp_path / "stateline-gpu")
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + build.INCLUDE, os.path.join(build.ROOT, "examples", "stateline_gpu.cpp"),
-                           "-L" + build.PKG, "-lslgpu", "-Wl,-rpath," + build.PKG, "-o", exe])
+    # stateline-gpu, the C++ host over the C-ABI: the reference's command line, csv files, table logger, checkpoints
+    exe = build.build_cli()
     w = configs.workload("config1")
-    c2 = configs.engine_config(w, sink="csv", seed=4)
+    c2 = configs.engine_config(w, seed=4)
+    assert "sink" not in c2["gpu"]  # the CLI defaults to csv like the reference
+    c2["gpu"].update(plugin=build.TARGETS_SO, entry="slgpu_plugin_demo_gauss")
     c2["outputPath"] = str(tmp_path / "demo-output")
     c2["nSamplesTotal"] = 200
+    c2["loggingRateSec"] = 0.0
     import json
-    (tmp_path / "cfg.json").write_text(json.dumps(c2))
-    out = subprocess.check_output([exe, "-c", str(tmp_path / "cfg.json"), "-p", build.TARGETS_SO, "-e", "slgpu_plugin_demo_gauss"])
-    summ = json.loads(out.decode().strip().splitlines()[-1])
+    (tmp_path / "cfg.json").write_text(json.dumps(c2, indent=2))
+    ck = str(tmp_path / "ck.slgpu")
+    out = subprocess.check_output([exe, "-c", str(tmp_path / "cfg.json"), "-p", "5555", "--checkpoint", ck]).decode()
+    summ = json.loads(out.strip().splitlines()[-1])
     assert summ["rounds"] == 100
     assert len(open(os.path.join(c2["outputPath"], "1.csv")).read().splitlines()) == 101
+    orc = oracle_for(w, seed=4)
+    orc.init_chains()
+    orc.run_rounds(100)
+    assert out.count("  ID    Length    MinEngy") >= 1 and orc.format_table() in out  # the final table is the oracle's
+    # resume for another 60 rounds, quietly: the files continue, no table is printed
+    c2["nSamplesTotal"] = 320
+    (tmp_path / "cfg2.json").write_text(json.dumps(c2))
+    out = subprocess.check_output([exe, "-c", str(tmp_path / "cfg2.json"), "-l", "-1", "--resume", ck]).decode()
+    assert json.loads(out.strip().splitlines()[-1])["rounds"] == 160 and "MinEngy" not in out
+    orc.run_rounds(60)
+    for s in range(w["S"]):
+        lines = open(os.path.join(c2["outputPath"], "%d.csv" % s)).read().splitlines()
+        assert lines == [O.csv_row(r, w["d"]) for r in orc.cold_rows(s)]
+    # errors: the reference's message for a missing config; a config without a plugin
+    r = subprocess.run([exe, "-c", str(tmp_path / "nope.json")], capture_output=True)
+    assert r.returncode == 1 and b"Could not find config file" in r.stderr
+    del c2["gpu"]["plugin"]
+    (tmp_path / "cfg3.json").write_text(json.dumps(c2))
+    assert subprocess.run([exe, "-c", str(tmp_path / "cfg3.json")], capture_output=True).returncode == 2
 
 
 def _full_state(eng, chains):
@@ -365,10 +386,21 @@ def test_checkpoint_keeps_the_rate_windows(tmp_path):
         eng.load_state(ck)
         eng.step_rounds(200)
         assert eng.format_table() == want
+    # the windows are logging only: a checkpoint with them loads into an engine that keeps none, and the other way
+    # round the windows start empty; the chains continue identically either way
     with engine_for(w, seed=2, sink="none") as eng:
-        with pytest.raises(sb.SlgpuError) as ei:
-            eng.load_state(ck)  # a checkpoint with windows does not fit an engine without them
-        assert ei.value.status == engine.E_CONFIG
+        eng.load_state(ck)
+        eng.step_rounds(200)
+        plain = eng.last_rows()
+        ck2 = tmp_path / "plain.slgpu"
+        eng.save_state(ck2)
+    with engine_for(w, seed=2, sink="none", windowRates=True) as eng:
+        eng.load_state(ck2)
+        assert np.array_equal(eng.last_rows(), plain)
+        cur, ar, sr = eng.logger()
+        assert not ar.any() and not sr.any()
+        eng.step_rounds(10)
+        assert eng.logger()[1].max() <= 1.0 and eng.rounds_done == 1310
 
 
 @pytest.mark.parametrize("threads", [1, 3, 16])
