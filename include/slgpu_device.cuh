@@ -222,13 +222,13 @@ struct ThreadMap {
   int T, lane, sl, t, base, spw;
   u32 s, c;
   bool active;
-  __device__ ThreadMap(const slgpu_step_params& p) {
+  __device__ ThreadMap(const slgpu_step_params& p, u32 block = blockIdx.x) {
     T = (int)p.n_temps;
     spw = 32 / T;
     lane = threadIdx.x & 31;
     sl = lane / T;
     t = lane - sl * T;
-    const u32 gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const u32 gw = block * (blockDim.x >> 5) + (threadIdx.x >> 5);
     s = gw * (u32)spw + (u32)sl;
     active = (sl < spw) && (s < p.n_stacks);
     if (sl >= spw) { /* idle tail lanes of a warp: keep every shuffle source inside the warp */

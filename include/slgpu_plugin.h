@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SLGPU_PLUGIN_ABI 2u
+#define SLGPU_PLUGIN_ABI 3u
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
 #define SLGPU_L_TILE 128u   /* chains per tile of the packed-L store (see slgpu_step_params.L) */

@@ -255,11 +255,24 @@ __device__ __forceinline__ double shaper_update_pair2(double* Lc, double* xs, in
 }
 
 /* chain of thread slot ct of this block under ThreadMap (only called for active slots) */
-__device__ __forceinline__ u32 thread_chain(const slgpu_step_params& p, int ct) {
+__device__ __forceinline__ u32 thread_chain(const slgpu_step_params& p, u32 blk, int ct) {
   const int T = (int)p.n_temps, spw = 32 / T, lane = ct & 31, sl = lane / T, t = lane - sl * T;
-  const u32 s = (blockIdx.x * (blockDim.x >> 5) + (u32)(ct >> 5)) * (u32)spw + (u32)sl;
+  const u32 s = (blk * (blockDim.x >> 5) + (u32)(ct >> 5)) * (u32)spw + (u32)sl;
   return s * (u32)T + (u32)t;
 }
+
+#ifdef SLGPU_STAMPS /* development: block-level time stamps (ns) into the round_flags buffer, 32 u64 per block */
+#define SLGPU_STAMP(k)                                                                        \
+  do {                                                                                        \
+    if (threadIdx.x == 0 && p.round_flags) {                                                  \
+      unsigned long long t_;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                   \
+      ((unsigned long long*)p.round_flags)[(size_t)blockIdx.x * 32 + (k)] = t_;               \
+    }                                                                                         \
+  } while (0)
+#else
+#define SLGPU_STAMP(k) do {} while (0)
+#endif
 
 /* dynamic shared memory of pt_step_fast_kernel */
 template <int D, int NT>
@@ -270,7 +283,8 @@ inline size_t fast_smem_bytes(unsigned n_temps) {
 
 template <class Lik, int D, int NT>
 __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(const slgpu_step_params p) {
-  const ThreadMap m(p);
+  const u32 blk = blockIdx.x; /* stack group of this block */
+  const ThreadMap m(p, blk);
   const int T = m.T;
   const size_t C = (size_t)p.n_stacks * p.n_temps;
   const bool active = m.active;
@@ -294,6 +308,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   __shared__ double s_nsc[NT];      /* result: new N scale, indexed by owning thread */
   __shared__ unsigned short s_owner[NT]; /* owning thread of the staged chain (its chain id follows from the thread map) */
   __shared__ int s_nacc[2];
+  SLGPU_STAMP(0);
   for (int i = tid; i < D; i += NT) {
     s_mn[i] = p.mn[i];
     s_mx[i] = p.mx[i];
@@ -330,6 +345,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   double lg_min_e = p.lg_min_energy[c];
   const double w3[3] = {s_w[3 * m.t], s_w[3 * m.t + 1], s_w[3 * m.t + 2]};
   const int W = (int)p.swap_interval;
+  SLGPU_STAMP(1);
 
   for (u32 it = 0; it < p.n_rounds; ++it) {
     const u64 r = p.round_begin + it;
@@ -403,13 +419,20 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
     }
     __syncthreads();
+    SLGPU_STAMP(2 + 3 * it);
     /* ================= phase B: compacted ProposalShaper updates ================= */
     {
       const int nacc = s_nacc[par];
       /* slot -> thread map: the staged chains are dealt round-robin to the warps (with few warps resident
        * per SM, parallel part-filled warps beat one full warp) */
 #if !defined(SLGPU_SLOTMAP_STRIDED) && !defined(SLGPU_SLOTMAP_CONTIGUOUS) /* measured on config #3: dense 74, strided 78, contiguous runs 95 us per round */
+#ifndef SLGPU_SLOT_FIXED /* measured on config #3: rotating 56.4 us per round, always warp 0 first 57.1 */
+      /* fill whole warps, but start at a different warp every round and block: a warp sits on a fixed scheduler,
+       * and always packing into warp 0 would load the same scheduler's FP64 pipe in every block of the SM */
+      const int slot = (tid + NT - 32 * (int)((it + blk) % (u32)(NT / 32))) & (NT - 1);
+#else
       const int slot = tid; /* fill the first warps completely */
+#endif
       const bool mine = slot < nacc;
 #elif defined(SLGPU_SLOTMAP_STRIDED)
       const int slot = (tid & 31) * (NT / 32) + (tid >> 5);
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #ifndef SLGPU_PHASEB_PAIR /* measured on config #3: one lane per staged chain 59.7 us per round, a lane pair 68.8 */
       if (mine) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
         const int own = s_owner[slot];
-        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, own), D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
+        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, blk, own), D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
                                              s_cnt[slot], p.prop_norm);
       }
 #else
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
        * in column u of s_z (every z is dead by now) */
       const unsigned pm = 3u << (m.lane & ~1);
       for (int u = tid >> 1; u < nacc; u += NT / 2) {
-        const double ns = shaper_update_pair2<D>(l_base(p.L, thread_chain(p, s_owner[u]), D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
+        const double ns = shaper_update_pair2<D>(l_base(p.L, thread_chain(p, blk, s_owner[u]), D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
                                                  p.prop_norm, tid & 1, pm);
         if ((tid & 1) == 0) s_nsc[s_owner[u]] = ns;
       }
@@ -439,9 +462,12 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       if (tid == 0) s_nacc[par ^ 1] = 0;
     }
     __syncthreads();
+    SLGPU_STAMP(3 + 3 * it);
     if (acc) nscale = s_nsc[tid];
     /* the table logger's per-round log: written here, where acc dies; the swap sweep below adds its two bits */
+#ifndef SLGPU_STAMPS
     if (p.round_flags && active) p.round_flags[(size_t)it * C + c] = (unsigned char)(acc ? 1 : 0);
+#endif
 
     /* ================= swap sweep, hottest pair first ================= */
     double mid_e = energy;
@@ -489,7 +515,9 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       accepted = new_acc;
       if (active && m.t < T - 1) {
         swap_type = my_swapped ? 1 : 2;
+#ifndef SLGPU_STAMPS
         if (p.round_flags) p.round_flags[(size_t)it * C + c] |= (unsigned char)(swap_type << 1);
+#endif
         double Pb[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) Pb[k] = p.p_beta[pidx(p, k, m.t, m.s)];
@@ -521,7 +549,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     {
       const double nn = (double)(r + 1);
       const double rnn = 1.0 / nn;
-      const u32 s0 = (blockIdx.x * (NT / 32) + (u32)(tid >> 5)) * (u32)m.spw; /* first stack of this warp */
+      const u32 s0 = (blk * (NT / 32) + (u32)(tid >> 5)) * (u32)m.spw; /* first stack of this warp */
       for (int task = m.lane; task < m.spw * D; task += 32) {
         const int sl = task / D, i = task - sl * D;
         const u32 sc = s0 + (u32)sl;
@@ -536,6 +564,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
         }
       }
     }
+    SLGPU_STAMP(4 + 3 * it);
   }
 
   if (active) {

@@ -1397,6 +1397,9 @@ slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
   return SLGPU_OK;
 }
 
+// development aid (tools/stamps.py): the device buffer of the per-round flags; not part of the documented ABI
+void* slgpu_debug_round_flags(slgpu_engine* e) { return e ? (void*)e->d_round_flags : nullptr; }
+
 size_t slgpu_format_row(const double* row, uint32_t d, char* out, size_t cap) { return format_row(row, d, out, cap); }
 
 slgpu_status slgpu_measure_fp64_peak(int device, double* tflops) {

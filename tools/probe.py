@@ -13,9 +13,13 @@ ap.add_argument("--stacks", type=int, default=None)
 ap.add_argument("--warm", type=int, default=200)
 ap.add_argument("--rounds", type=int, default=500)
 ap.add_argument("--sink", default="device")
+ap.add_argument("--swap", type=int, default=0, help="override swapInterval")
+ap.add_argument("--mrl", type=int, default=64, help="gpu.maxRoundsPerLaunch")
 a = ap.parse_args()
 w = configs.workload(a.workload, S=a.stacks)
-with Engine(configs.engine_config(w, sink=a.sink, overwrite=True), plugin=w["plugin"], payload=w["payload"]) as e:
+if a.swap:
+    w["swapInterval"] = a.swap
+with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLaunch=a.mrl), plugin=w["plugin"], payload=w["payload"]) as e:
     e.init_chains()
     e.step_rounds(a.warm)
     e.sync()
@@ -23,10 +27,11 @@ with Engine(configs.engine_config(w, sink=a.sink, overwrite=True), plugin=w["plu
         e.timer_start()
         e.step_rounds(a.rounds)
         ms = e.timer_stop()
+        kms, kn = e.timer_step_kernel()
         e.sync()
         cs = w["S"] * w["T"] * a.rounds
         print(json.dumps({"workload": a.workload, "S": w["S"], "T": w["T"], "d": w["d"], "rounds": a.rounds, "ms": ms,
-                          "us_per_round": 1e3 * ms / a.rounds, "chain_steps_per_s": cs / (ms * 1e-3)}))
+                          "us_per_round": 1e3 * ms / a.rounds, "kernel_us_per_round": 1e3 * kms / a.rounds, "launches": kn, "chain_steps_per_s": cs / (ms * 1e-3)}))
     s = e.summary()
     print(json.dumps({k: s[k] for k in ("accept_rate", "swap_rate", "sigma", "beta")}))
     print("rhat mean", sum(s["rhat"]) / max(1, len(s["rhat"])))
