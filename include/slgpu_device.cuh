@@ -201,6 +201,17 @@ struct StaticJobs<L, D, std::void_t<decltype(L::template static_job_types<D>())>
   static constexpr int value = L::template static_job_types<D>();
 };
 
+/* Optional: a functor may evaluate all job types of one point with a whole warp,
+ *     __device__ void warp_jobs(const double* x, u32 d, u32 n_jobs, int lane, double* values, double* scratch) const;
+ * It is called by the 32 lanes of a warp together; x, values ([n_jobs]) and scratch ([d]) are per-warp shared memory.
+ * When it returns, values[j] must hold exactly what operator()(j, x, d) returns (same operations in the same order)
+ * and be visible to every lane (end with __syncwarp()).  The warp-per-chain kernel (d > 32) uses it: a likelihood on
+ * one lane per job type leaves the other lanes idle. */
+template <class L, class = void>
+struct HasWarpJobs : std::false_type {};
+template <class L>
+struct HasWarpJobs<L, std::void_t<decltype(&L::warp_jobs)>> : std::true_type {};
+
 /* base of chain c's packed L inside its 128-chain tile; consecutive entries are SLGPU_L_TILE doubles apart */
 __device__ __forceinline__ double* l_base(double* L, u32 c, u32 nL) {
   return L + (size_t)(c / SLGPU_L_TILE) * nL * SLGPU_L_TILE + (c % SLGPU_L_TILE);
@@ -605,7 +616,7 @@ template <class Lik, int D>
 int launch_step_t(const slgpu_step_params* p, void* stream) {
   if (SLGPU_L_LAYOUT(p->n_dims) == SLGPU_L_COLMAJOR) { /* d > 32: one warp per chain, whole stacks per block */
     const unsigned spb = warp_stacks_per_block(p->n_temps), warps = spb * p->n_temps;
-    const size_t smem = warp_smem_bytes(p, warps);
+    const size_t smem = warp_smem_bytes(p, warps, HasWarpJobs<Lik>::value);
     const unsigned grid = (p->n_stacks + spb - 1) / spb, threads = warps * 32;
     const int rm = (int)(p->n_dims + 31) / 32;
 #define SLGPU_WARP_LAUNCH(RMV, MAXTV)                                                                                     \

@@ -12,8 +12,8 @@
  *     32-slot order (slot l = rows l, l+32, ...; halving tree = __shfl_down), so results equal the oracle's bit for bit;
  *   - accept / reject is warp-uniform: the shaper update runs in place without divergence;
  *   - the chain's scalars are replicated over the lanes; normals, proposal and the running jump go through a
- *     per-warp vector in shared memory; the functor evaluates job types lane, lane+32, ... and every lane adds
- *     the J values in job order;
+ *     per-warp vector in shared memory; the functor evaluates job types lane, lane+32, ... (or all of them with the
+ *     whole warp, if it has warp_jobs) and every lane adds the J values in job order;
  *   - a block holds whole stacks (T warps each); the swap sweep of a stack goes through shared memory.
  */
 #ifndef SLGPU_STEP_WARP_CUH
@@ -31,10 +31,12 @@ namespace slgpu {
 #endif
 constexpr int kWarpGemvUnroll = SLGPU_WARP_GEMV_UNROLL;
 
-/* dynamic shared memory: per warp a vector [d+1] and [J] job values; per stack the swap scratch */
-inline size_t warp_smem_bytes(const slgpu_step_params* p, unsigned warps) {
+/* dynamic shared memory: per warp a vector [d+1] and [J] job values; per stack the swap scratch; per warp a [d]
+ * scratch vector when the functor has warp_jobs */
+inline size_t warp_smem_bytes(const slgpu_step_params* p, unsigned warps, bool warp_jobs) {
   const size_t d = p->n_dims, J = p->n_job_types, T = p->n_temps, stacks = warps / T;
-  return (warps * (d + 1) + warps * J + stacks * (3 * T + T * d)) * sizeof(double) + stacks * T * sizeof(int);
+  return (warps * (d + 1) + warps * J + stacks * (3 * T + T * d) + (warp_jobs ? warps * d : 0)) * sizeof(double) +
+         (stacks * T + 1) / 2 * 2 * sizeof(int);
 }
 
 /* stacks per block: as many whole stacks as fit 8 warps (at least one) */
@@ -63,6 +65,9 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
   double* const sw_u = sw + 2 * T;   /* [T] swap uniforms */
   double* const sw_x = sw + 3 * T;   /* [T][d] samples */
   int* const sw_acc = (int*)(s_dyn + (size_t)nwarps * (d + 1) + (size_t)nwarps * J + (size_t)spb * (3 * T + T * d)) + sl * T;
+  /* functor scratch (HasWarpJobs): behind the ints, 8-byte aligned */
+  double* const wj = s_dyn + (size_t)nwarps * (d + 1) + (size_t)nwarps * J + (size_t)spb * (3 * T + T * d) + (size_t)(spb * T + 1) / 2 +
+                     (size_t)warp * d;
   __shared__ double s_mn[SLGPU_MAX_DIMS], s_mx[SLGPU_MAX_DIMS], s_n0[SLGPU_MAX_DIMS], s_rd[SLGPU_MAX_DIMS];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
   for (int i = tid; i < d; i += blockDim.x) {
@@ -155,8 +160,12 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       }
       __syncwarp();
       /* ---- energy: job types lane, lane+32, ...; every lane adds the J values in job order ---- */
-      for (int jj = lane; jj < J; jj += 32) fv[jj] = lik((u32)jj, vec, (u32)d);
-      __syncwarp();
+      if constexpr (HasWarpJobs<Lik>::value) {
+        lik.warp_jobs(vec, (u32)d, (u32)J, lane, fv, wj);
+      } else {
+        for (int jj = lane; jj < J; jj += 32) fv[jj] = lik((u32)jj, vec, (u32)d);
+        __syncwarp();
+      }
       double e_new = 0.0;
       for (int jj = 0; jj < J; ++jj) e_new += fv[jj];
       /* ---- acceptProposal (chainarray.cpp:30-45), append (:94-121) ---- */

@@ -48,7 +48,7 @@ def workload(name, S=None, T=None):
         d, J = 100, 4
         U = np.triu(gauss_corr_U(d, 4))
         w = dict(S=1024, T=8, J=J, mn=[-20.0] * d, mx=[20.0] * d, plugin="gauss_corr",
-                 payload=np.concatenate([[float(J)], U.ravel()]), oracle_target=T_GAUSS_CORR, oracle_params=U.ravel())
+                 payload=np.concatenate([[float(J)], U.ravel(), U.T.ravel()]), oracle_target=T_GAUSS_CORR, oracle_params=U.ravel())
     elif name in ("rosenbrock50", "config5"):
         d, J = 50, 7
         w = dict(S=8192, T=16, J=J, mn=[-5.0] * d, mx=[5.0] * d, plugin="rosenbrock", payload=np.array([float(J)]),

@@ -55,7 +55,7 @@ struct GaussFact {
   }
 };
 
-/* config #4 -- correlated Gaussian 0.5*|U x|^2 split in J row blocks; payload = {J as double, U[d*d] row-major upper} */
+/* config #4 -- correlated Gaussian 0.5*|U x|^2 split in J row blocks; payload = {J as double, U[d*d] row-major upper, transpose(U)[d*d]} */
 struct GaussCorr {
   const double* prm;
   __device__ explicit GaussCorr(const void* payload) : prm((const double*)payload) {}
@@ -72,6 +72,38 @@ struct GaussCorr {
       acc = fma(dot, dot, acc);
     }
     return 0.5 * acc;
+  }
+  /* All job types with one warp (d <= 128).  Lane l owns rows l, l+32, ...: every row's dot product is still its own
+   * fma chain over ascending c, the rows of a lane run interleaved, and U is read through its transpose (the second
+   * matrix of the payload) so that the lanes of a row group read consecutive addresses.  Then lane j folds the rows
+   * of job j in row order. */
+  __device__ void warp_jobs(const double* x, u32 d, u32 n_jobs, int lane, double* values, double* dots) const {
+    const double* Ut = prm + 1 + (size_t)d * d; /* Ut[c * d + r] = U[r * d + c] */
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (u32 c = 0; c < d; ++c) {
+      const double xc = x[c];
+      const double* col = Ut + (size_t)c * d;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const u32 r = (u32)lane + 32u * (u32)m;
+        if (32u * (u32)m <= c && r <= c) dot[m] = fma(__ldg(col + r), xc, dot[m]); /* first test is warp-uniform */
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const u32 r = (u32)lane + 32u * (u32)m;
+      if (r < d) dots[r] = dot[m];
+    }
+    __syncwarp();
+    const u32 per = (d + n_jobs - 1) / n_jobs;
+    for (u32 job = (u32)lane; job < n_jobs; job += 32) {
+      const u32 r0 = job * per;
+      const u32 r1 = (r0 + per < d) ? r0 + per : d;
+      double acc = 0.0;
+      for (u32 r = r0; r < r1; ++r) acc = fma(dots[r], dots[r], acc);
+      values[job] = 0.5 * acc;
+    }
+    __syncwarp();
   }
 };
 
@@ -92,6 +124,25 @@ struct Rosenbrock {
       acc += (100.0 * (a * a) + b * b) / 20.0;
     }
     return acc;
+  }
+  /* all job types with one warp: the terms are dealt to the lanes, then lane j adds the terms of job j in order */
+  __device__ void warp_jobs(const double* x, u32 d, u32 n_jobs, int lane, double* values, double* terms) const {
+    const u32 nterm = d - 1;
+    for (u32 i = (u32)lane; i < nterm; i += 32) {
+      const double a = x[i + 1] - x[i] * x[i];
+      const double b = 1.0 - x[i];
+      terms[i] = (100.0 * (a * a) + b * b) / 20.0;
+    }
+    __syncwarp();
+    const u32 per = (nterm + n_jobs - 1) / n_jobs;
+    for (u32 job = (u32)lane; job < n_jobs; job += 32) {
+      const u32 i0 = job * per;
+      const u32 i1 = (i0 + per < nterm) ? i0 + per : nterm;
+      double acc = 0.0;
+      for (u32 i = i0; i < i1; ++i) acc += terms[i];
+      values[job] = acc;
+    }
+    __syncwarp();
   }
 };
 
