@@ -149,10 +149,10 @@ def run_reference(args, rank, world):
     kw = dict(S=w["S"], T=w["T"], J=w["J"], swap_interval=w["swapInterval"], opt_accept=w["optAccept"], opt_swap=w["optSwap"],
               mn=w["mn"], mx=w["mx"], target=w["oracle_target"], target_params=w["oracle_params"],
               schedule=O.SCHED_SEQUENTIAL, rng_mode=O.RNG_PHILOX, seed=1234)
-    # size one step so that (warmup + steps) steps take about 60 s
+    # size one step so that (warmup + steps) steps take about --ref-seconds (60 s)
     secs, steps = O.time_server_workers(n_workers, 10, **kw)
     per_round = secs / 10
-    rounds_per_step = max(1, int(60.0 / max(per_round * (args.steps + args.warmup), 1e-9)))
+    rounds_per_step = max(1, int(args.ref_seconds / max(per_round * (args.steps + args.warmup), 1e-9)))
     for _ in range(args.warmup):
         O.time_server_workers(n_workers, rounds_per_step, **kw)
     tot_s, tot_steps = 0.0, 0
@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU seconds the whole run is sized for")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
