@@ -152,17 +152,28 @@ def test_csv_row_format():
 
 
 # ---- golden fixture: oracle output recorded by tests/golden/make_golden.py -----------------------------
-def test_golden_fixture():
-    g = json.load(open(os.path.join(HERE, "golden", "oracle_config1_seed7.json")))
-    s = O.Sampler(S=2, T=5, J=3, swap_interval=10, opt_accept=0.234, opt_swap=0.3874, mn=[-10, 0, -10, -10],
-                  mx=[10, 10, 10, 2], target=O.TARGET_DEMO_GAUSS, schedule=O.SCHED_BATCHED, rng_mode=O.RNG_PHILOX, seed=7)
+GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".json"))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fixture(name):
+    from helpers import oracle_for
+    from stateline_b200 import configs
+    g = json.load(open(os.path.join(HERE, "golden", name + ".json")))
+    w = configs.workload(g["workload"], **g["workload_args"])
+    s = oracle_for(w, seed=g["seed"])
     s.init_chains()
     s.run_rounds(g["rounds"])
-    rows = s.last_rows()
-    assert np.array_equal(rows, np.array(g["last_rows"]))
+    assert np.array_equal(s.last_rows(), np.array(g["last_rows"]))
     assert np.array_equal(s.cold_rows(0)[-3:], np.array(g["cold_rows_stack0_tail"]))
     sig, beta = s.sigma_beta()
     assert np.array_equal(sig, np.array(g["sigma"])) and np.array_equal(beta, np.array(g["beta"]))
+    assert np.array_equal(s.rhat(), np.array(g["rhat"])) and s.format_table() == g["table"]
+
+
+def test_golden_covers_the_five_workloads():
+    assert len(GOLDEN) == 5 and {json.load(open(os.path.join(HERE, "golden", n + ".json")))["workload"] for n in GOLDEN} == {
+        "config1", "config2", "config3", "config4", "config5"}
 
 
 # ---- schedules: the reference order (sequential) and the launch-granular one (batched) agree statistically ----

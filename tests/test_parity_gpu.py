@@ -107,16 +107,22 @@ def test_step_kernel_variants_agree(monkeypatch):
             assert np.array_equal(a, b)
 
 
-def test_golden_fixture():
-    """Committed oracle output (tests/golden/make_golden.py): the GPU reproduces it bit for bit."""
-    g = json.load(open(os.path.join(HERE, "golden", "oracle_config1_seed7.json")))
-    w = configs.workload("config1")
-    with engine_for(w, seed=7) as eng:
+GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".json"))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fixture(name):
+    """Committed oracle output on the five workloads (tests/golden/make_golden.py): the GPU reproduces it bit for bit,
+    the printed logger table included."""
+    g = json.load(open(os.path.join(HERE, "golden", name + ".json")))
+    w = configs.workload(g["workload"], **g["workload_args"])
+    with engine_for(w, seed=g["seed"], windowRates=True) as eng:
         eng.init_chains()
         eng.step_rounds(g["rounds"])
         assert np.array_equal(eng.last_rows(), np.array(g["last_rows"]))
         sig, beta = eng.sigma_beta()
         assert np.array_equal(sig, np.array(g["sigma"])) and np.array_equal(beta, np.array(g["beta"]))
+        assert np.array_equal(eng.rhat(), np.array(g["rhat"])) and eng.format_table() == g["table"]
         rows = eng.drain().reshape(g["rounds"] + 1, w["S"], w["d"] + 5)
         assert np.array_equal(rows[-3:, 0], np.array(g["cold_rows_stack0_tail"]))
 
