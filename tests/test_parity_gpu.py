@@ -186,6 +186,48 @@ def test_edge_shapes_bit_exact(S, T, d, J, rounds):
             assert np.array_equal(rows[:, s], orc.cold_rows(s))
 
 
+def _random_shapes(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        T = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 11, 16, 32]))
+        d = int(rng.choice([1, 2, 3, 4, 7, 12, 20, 31, 32, 33, 40, 63, 64, 65, 100, 128]))
+        S = int(rng.integers(1, 40 if d <= 32 else 4))
+        J = int(rng.integers(1, 6))
+        swap = int(rng.integers(1, 9))
+        adapt = int(rng.choice([swap, swap, 1, 3, 7]))
+        mrl = int(rng.choice([64, 64, 1, 2, 5]))
+        rounds = int(rng.integers(8, 40 if d <= 32 else 14))
+        out.append((S, T, d, J, swap, adapt, mrl, rounds, bool(rng.integers(0, 2)), int(rng.integers(0, 1000))))
+    return out
+
+
+@pytest.mark.parametrize("S,T,d,J,swap,adapt,mrl,rounds,use_initial,seed", _random_shapes(28, 2026))
+def test_random_shapes_bit_exact(S, T, d, J, swap, adapt, mrl, rounds, use_initial, seed):
+    """A seeded sweep over shapes and schedules: stack / ladder / dimension / job counts, swap interval, an adapt
+    interval different from it, launches cut at 1, 2, 5 rounds, fixed initial state -- always the oracle's bits."""
+    mn = [-2.0 - 0.05 * i for i in range(d)]
+    mx = [1.5 + 0.1 * i for i in range(d)]
+    w = dict(S=S, T=T, d=d, J=J, mn=mn, mx=mx, swapInterval=swap, optAccept=0.25, optSwap=0.4, plugin="demo_gauss", payload=None,
+             oracle_target=configs.T_DEMO_GAUSS, oracle_params=None)
+    initial = [0.1 * ((i % 5) - 2) for i in range(d)] if use_initial else None
+    orc = oracle_for(w, seed=seed, stack_offset=seed % 7, adapt_interval=adapt, initial=initial)
+    orc.init_chains()
+    orc.run_rounds(rounds)
+    cfg = configs.engine_config(w, seed=seed, sink="host", stackOffset=seed % 7, adaptInterval=adapt, maxRoundsPerLaunch=mrl,
+                                hostRingRounds=64)
+    if use_initial:
+        cfg["useInitial"], cfg["initial"] = True, initial
+    from stateline_b200 import Engine
+    with Engine(cfg, plugin="demo_gauss") as eng:
+        eng.init_chains()
+        eng.step_rounds(rounds)
+        _compare(eng, orc, w, "random shape S=%d T=%d d=%d J=%d swap=%d adapt=%d mrl=%d" % (S, T, d, J, swap, adapt, mrl))
+        rows = eng.drain().reshape(rounds + 1, S, d + 5)
+        for s in range(S):
+            assert np.array_equal(rows[:, s], orc.cold_rows(s))
+
+
 def test_zero_rounds_and_empty_run():
     w = configs.workload("config1")
     with engine_for(w, seed=1) as eng:
