@@ -127,6 +127,7 @@ struct slgpu_engine {
   slgpu_step_params P{};
   double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
   void* d_payload = nullptr;
+  unsigned int* d_ticket = nullptr;    // last-block ticket of k_tier_adapt
   unsigned char* d_round_flags = nullptr;  // windowRates: [seg_rounds][C] per-round accept / swap flags of a launch
   uint32_t *d_win_sig = nullptr, *d_win_beta = nullptr, *d_win_cnt = nullptr, *d_win_sum = nullptr;
   double *d_rp_z = nullptr, *d_rp_umh = nullptr, *d_rp_uswap = nullptr, *d_rp_xinit = nullptr;
@@ -505,10 +506,10 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
 
 slgpu_status adapt_point(slgpu_engine* e) {
   const uint32_t T = e->cfg.nTemps;
-  slgpu_tier::k_tier_reduce<<<dim3(T, 2, 9), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_sums);
-  slgpu_tier::k_tier_solve<<<1, 64, 0, e->compute>>>(e->d_sums, T, e->d_models, e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
+  slgpu_tier::k_tier_adapt<<<dim3(T, 2, 9), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_sums, e->d_ticket, e->d_models,
+                                                                  e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
   CU_TRY(cudaGetLastError());
-  e->launches += 2;
+  e->launches += 1;
   return SLGPU_OK;
 }
 
@@ -623,7 +624,10 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     for (uint32_t i = 0; i < d; ++i) n0[i] = range[i] / P.prop_norm;
     double *d_mn, *d_mx, *d_n0, *d_init = nullptr;
     slgpu_status s2;
-#define TRY_ST(x) if ((s2 = (x)) != SLGPU_OK) return s2
+#define TRY_ST(x)                           \
+  do {                                      \
+    if ((s2 = (x)) != SLGPU_OK) return s2;  \
+  } while (0)
     TRY_ST(dev_alloc(e, &d_mn, d)); TRY_ST(upload(d_mn, cfg.mn));
     TRY_ST(dev_alloc(e, &d_mx, d)); TRY_ST(upload(d_mx, cfg.mx));
     TRY_ST(dev_alloc(e, &d_n0, d)); TRY_ST(upload(d_n0, n0));
@@ -644,6 +648,8 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     TRY_ST(dev_alloc(e, &e->d_sig_w, (size_t)3 * T));
     TRY_ST(dev_alloc(e, &e->d_ladder, T));
     TRY_ST(dev_alloc(e, &e->d_sums, (size_t)2 * T * 9));
+    TRY_ST(dev_alloc(e, &e->d_ticket, 1));
+    CU_TRY(cudaMemset(e->d_ticket, 0, sizeof(unsigned int)));
     P.sig_w = e->d_sig_w;
     P.ladder = e->d_ladder;
     {
@@ -681,8 +687,11 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
       const size_t seg_doubles = (size_t)e->seg_rounds * S * e->row_w;
       const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;
       for (int i = 0; i < kSegments; ++i) {
-        if (i < nseg) TRY_ST(dev_alloc(e, &e->seg[i].dev, seg_doubles));
-        else e->seg[i].dev = e->seg[0].dev;
+        if (i < nseg) {
+          TRY_ST(dev_alloc(e, &e->seg[i].dev, seg_doubles));
+        } else {
+          e->seg[i].dev = e->seg[0].dev;
+        }
         CU_TRY(cudaEventCreateWithFlags(&e->seg[i].written, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&e->seg[i].copied, cudaEventDisableTiming));
       }

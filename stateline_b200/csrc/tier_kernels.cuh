@@ -154,10 +154,13 @@ __global__ void k_tier_init(double* models, double* sig_w, double* ladder, uint3
 // grid (T, 2, 9), 256 threads: block (t, which, k) sums statistic k of tier t over the stacks in the
 // fixed shape of the oracle's reduce_tree256 (slot i adds stacks i, i+256, ... in order, then a halving
 // tree), clears it, and writes sums[(which * T + t) * 9 + k].
-__global__ void __launch_bounds__(256) k_tier_reduce(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* sums) {
+__global__ void __launch_bounds__(256) k_tier_adapt(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* sums,
+                                                    unsigned int* ticket, double* models, double* sig_w, double opt_swap,
+                                                    double* ladder) {
   const uint32_t t = blockIdx.x, which = blockIdx.y, k = blockIdx.z, tid = threadIdx.x;
   double* P = (which ? p_beta : p_sig) + ((size_t)k * T + t) * S;
   __shared__ double a[256];
+  __shared__ bool last;
   double acc = 0.0;
   for (uint32_t m = tid; m < S; m += 256) {
     acc += P[m];
@@ -169,21 +172,27 @@ __global__ void __launch_bounds__(256) k_tier_reduce(double* p_sig, double* p_be
     if (tid < s) a[tid] += a[tid + s];
     __syncthreads();
   }
-  if (tid == 0) sums[(size_t)(which * T + t) * 9 + k] = a[0];
-}
-
-// one block, >= 2T threads: thread (which, t) folds the summed statistics into its model and re-solves;
-// then thread 0 rebuilds the ladder.
-__global__ void k_tier_solve(const double* sums, uint32_t T, double* models, double* sig_w, double opt_swap, double* ladder) {
-  const uint32_t i = threadIdx.x;
-  if (i < 2 * T) {
-    double* m = models + (size_t)i * kModelStride;
-    model_update_batched(m, sums + (size_t)i * 9);
-    if (i < T)
-      for (int j = 0; j < 3; ++j) sig_w[3 * i + j] = m[12 + j];
+  // The block that finishes last folds the 2T x 9 sums into the models (one thread per model) and rebuilds the
+  // ladder: one launch per adapt point instead of a reduce and a one-block solve behind it.
+  if (tid == 0) {
+    sums[(size_t)(which * T + t) * 9 + k] = a[0];
+    __threadfence();
+    const unsigned int n = gridDim.x * gridDim.y * gridDim.z;
+    last = atomicInc(ticket, n - 1) == n - 1;  // wraps to 0 for the next adapt point
   }
   __syncthreads();
-  if (i == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
+  if (!last) return;
+  __threadfence();
+  if (tid < 2 * T) {
+    double mine[9];
+    for (int j = 0; j < 9; ++j) mine[j] = __ldcg(sums + (size_t)tid * 9 + j);
+    double* m = models + (size_t)tid * kModelStride;
+    model_update_batched(m, mine);
+    if (tid < T)
+      for (int j = 0; j < 3; ++j) sig_w[3 * tid + j] = m[12 + j];
+  }
+  __syncthreads();
+  if (tid == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
 }
 
 // The acceptance windows of RegressionAdapter::update (adaptive.cpp:80-90), logging only: every chain keeps the last

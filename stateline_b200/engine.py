@@ -55,7 +55,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build_engine()
+    path = os.environ.get("SLGPU_ENGINE_SO") or _build.build_engine()  # env: development A/B builds
     L = C.CDLL(path)
     L.slgpu_last_error.restype = C.c_char_p
     L.slgpu_version.restype = C.c_char_p

@@ -228,6 +228,29 @@ def test_random_shapes_bit_exact(S, T, d, J, swap, adapt, mrl, rounds, use_initi
             assert np.array_equal(rows[:, s], orc.cold_rows(s))
 
 
+def test_one_round_launches_keep_their_rows():
+    """Launches cut to a single round run back to back while the drain stream still copies the previous
+    segment: the row segments must be distinct buffers (they once aliased, and a late copy picked up the next
+    round's rows about four runs in five).  Five runs of the racy shape, every cold row against the oracle."""
+    S, T, d, J, rounds = 37, 32, 4, 5, 27
+    mn = [-2.0 - 0.05 * i for i in range(d)]
+    mx = [1.5 + 0.1 * i for i in range(d)]
+    w = dict(S=S, T=T, d=d, J=J, mn=mn, mx=mx, swapInterval=8, optAccept=0.25, optSwap=0.4, plugin="demo_gauss", payload=None,
+             oracle_target=configs.T_DEMO_GAUSS, oracle_params=None)
+    orc = oracle_for(w, seed=345, stack_offset=2, adapt_interval=3)
+    orc.init_chains()
+    orc.run_rounds(rounds)
+    want = np.stack([orc.cold_rows(s) for s in range(S)], axis=1)
+    from stateline_b200 import Engine
+    for _ in range(5):
+        cfg = configs.engine_config(w, seed=345, sink="host", stackOffset=2, adaptInterval=3, maxRoundsPerLaunch=1, hostRingRounds=64)
+        with Engine(cfg, plugin="demo_gauss") as eng:
+            eng.init_chains()
+            eng.step_rounds(rounds)
+            rows = eng.drain().reshape(rounds + 1, S, d + 5)
+        assert np.array_equal(rows, want)
+
+
 def test_zero_rounds_and_empty_run():
     w = configs.workload("config1")
     with engine_for(w, seed=1) as eng:
