@@ -23,7 +23,7 @@ namespace slgpu {
 
 /* row groups per lane: RM = ceil(d / 32) is a template parameter (2, 3 or 4) so that small d carries no dead rows */
 #ifndef SLGPU_WARP_REGS
-#define SLGPU_WARP_REGS 32 /* register budget per thread: 65536 / budget threads resident per SM */
+#define SLGPU_WARP_REGS 64 /* register budget per thread: 65536 / budget threads resident per SM */
 #endif
 #define SLGPU_WARP_MINBLOCKS(maxt) (65536 / ((maxt) * SLGPU_WARP_REGS))
 #ifndef SLGPU_WARP_GEMV_UNROLL
@@ -41,6 +41,95 @@ inline size_t warp_smem_bytes(const slgpu_step_params* p, unsigned warps, bool w
 
 /* stacks per block: as many whole stacks as fit 8 warps (at least one) */
 inline unsigned warp_stacks_per_block(unsigned n_temps) { return n_temps >= 8 ? 1u : 8u / n_temps; }
+
+/* ---- column sweeps of the warp kernel.  Lp = Lg + lane; off_k = ck - k (ck = k*d - k(k-1)/2), so that L(j,k) with
+ * j = lane + 32m is Lp[off_k + 32m] and off_{k+1} = off_k + d - k - 1.  The sweeps are cut at the row-group
+ * boundaries (columns 32G .. 32G+31) so that which row groups take part is known at compile time. ---- */
+
+/* raw column k, rows j >= k of this lane (0 elsewhere); any k */
+template <int RM>
+__device__ __forceinline__ void warp_load_col(double* dst, const double* Lp, int off, int k, int lane, int d) {
+#pragma unroll
+  for (int m = 0; m < RM; ++m) {
+    const int j = lane + 32 * m;
+    dst[m] = (32 * m + 31 >= k && j >= k && j < d) ? Lp[off + 32 * m] : 0.0;
+  }
+}
+
+/* proposal GEMV, columns of row group G: a_j = fma(N_jk, z_k, a_j), k ascending */
+template <int RM, int G>
+__device__ __forceinline__ void warp_gemv_group(const double* Lp, int& off, const double* vec, const double* s_n0, double nscale,
+                                                bool fresh, int lane, int d, double* a) {
+  const int k1 = (32 * G + 32 < d) ? 32 * G + 32 : d;
+#pragma unroll kWarpGemvUnroll
+  for (int k = 32 * G; k < k1; ++k) {
+    const double zk = vec[k];
+    const double n0k = s_n0[k];
+#pragma unroll
+    for (int m = G; m < RM; ++m) {
+      const int j = lane + 32 * m;
+      if ((m > G || j >= k) && j < d) {
+        double njk = Lp[off + 32 * m] * nscale;
+        if (m == G && j == k) njk = fresh ? n0k : njk + 1e-4;
+        a[m] = fma(njk, zk, a[m]);
+      }
+    }
+    off += d - k - 1;
+  }
+  if constexpr (G + 1 < RM) {
+    if (k1 < d) warp_gemv_group<RM, G + 1>(Lp, off, vec, s_n0, nscale, fresh, lane, d, a);
+  }
+}
+
+/* rank-1 sweep of ProposalShaper::update (adaptive.cpp:184-197), columns of row group G.  cur / nx1 hold the raw
+ * columns k and k+1 (loaded two columns ahead of their use: a column's loads never depend on earlier columns'
+ * stores); the column head (old diagonal, x_k) comes from the owning lane by shuffle, not from memory. */
+template <int RM, int G>
+__device__ __forceinline__ void warp_shaper_group(double* Lp, int& off, int& off1, double* cur, double* nx1, double scale, int lane, int d,
+                                                  double* xs, double* fr) {
+  const double eps = 1e-18;
+  const int k1 = (32 * G + 32 < d) ? 32 * G + 32 : d;
+#pragma unroll 1
+  for (int k = 32 * G; k < k1; ++k) {
+    double nx2[RM];
+    const int off2 = off1 + d - k - 2;
+    warp_load_col<RM>(nx2, Lp, off2, (k + 2 < d) ? k + 2 : 0x7fff, lane, d); /* past the last column: nothing is loaded */
+    const double xk = __shfl_sync(0xffffffffu, xs[G], k & 31);
+    const double Lkk = __shfl_sync(0xffffffffu, cur[G], k & 31) * scale;
+    const double V = smax(eps, Lkk);
+    const double rV = 1.0 / V;
+    const double rr = sqrt(V * V + xk * xk);
+    const double cc = div_by(rr, V, rV);
+    const double ss = div_by(xk, V, rV);
+    const double rc = 1.0 / cc;
+#pragma unroll
+    for (int m = G; m < RM; ++m) {
+      const int j = lane + 32 * m;
+      if (j < d) {
+        if (m == G && j == k) {
+          Lp[off + 32 * m] = rr;
+          fr[m] = fma(rr, rr, fr[m]); /* the diagonal closes row k's sum */
+        } else if (m > G || j > k) {
+          double Ljk = cur[m] * scale;
+          Ljk = div_by(Ljk + ss * xs[m], cc, rc);
+          Lp[off + 32 * m] = Ljk;
+          xs[m] = cc * xs[m] - ss * Ljk;
+          fr[m] = fma(Ljk, Ljk, fr[m]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < RM; ++m) {
+      cur[m] = nx1[m];
+      nx1[m] = nx2[m];
+    }
+    off = off1;
+    off1 = off2;
+  }
+  if constexpr (G + 1 < RM) {
+    if (k1 < d) warp_shaper_group<RM, G + 1>(Lp, off, off1, cur, nx1, scale, lane, d, xs, fr);
+  }
+}
 
 template <class Lik, int RM, int MAXT>
 __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp_kernel(const slgpu_step_params p) {
@@ -132,22 +221,8 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
 #pragma unroll
       for (int m = 0; m < RM; ++m) a[m] = 0.0;
       {
-        size_t ck = 0;
-#pragma unroll kWarpGemvUnroll
-        for (int k = 0; k < d; ++k) {
-          const double zk = vec[k];
-          const double n0k = s_n0[k];
-#pragma unroll
-          for (int m = 0; m < RM; ++m) {
-            const int j = lane + 32 * m;
-            if (32 * m + 31 >= k && j >= k && j < d) {
-              double njk = Lg[ck + (size_t)(j - k)] * nscale;
-              if (j == k) njk = fresh ? n0k : njk + 1e-4;
-              a[m] = fma(njk, zk, a[m]);
-            }
-          }
-          ck += (size_t)(d - k);
-        }
+        int off = 0;
+        warp_gemv_group<RM, 0>(Lg + lane, off, vec, s_n0, nscale, fresh, lane, d, a);
       }
       __syncwarp(); /* z fully consumed: the vector takes the proposal */
 #pragma unroll
@@ -200,46 +275,17 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
         const double rsq = 1.0 / sq;
         const double scale = sqrt((sh_count - 1.0) / sh_count);
         double fr[RM];
-        __syncwarp();
 #pragma unroll
         for (int m = 0; m < RM; ++m) {
-          const int j = lane + 32 * m;
           xs[m] = div_by(xs[m], sq, rsq);
           fr[m] = 0.0;
-          if (j < d) vec[j] = xs[m];
         }
-        __syncwarp();
-        size_t ck = 0;
-        for (int k = 0; k < d; ++k) {
-          const double xk = vec[k];
-          const double Lkk = Lg[ck] * scale;
-          const double V = smax(eps, Lkk);
-          const double rV = 1.0 / V;
-          const double rr = sqrt(V * V + xk * xk);
-          const double cc = div_by(rr, V, rV);
-          const double ss = div_by(xk, V, rV);
-          const double rc = 1.0 / cc;
-          __syncwarp();
-#pragma unroll
-          for (int m = 0; m < RM; ++m) {
-            const int j = lane + 32 * m;
-            if (32 * m + 31 >= k && j < d) {
-              if (j == k) {
-                Lg[ck] = rr;
-                fr[m] = fma(rr, rr, fr[m]); /* the diagonal closes row k's sum */
-              } else if (j > k) {
-                const size_t o = ck + (size_t)(j - k);
-                double Ljk = Lg[o] * scale;
-                Ljk = div_by(Ljk + ss * xs[m], cc, rc);
-                Lg[o] = Ljk;
-                xs[m] = cc * xs[m] - ss * Ljk;
-                fr[m] = fma(Ljk, Ljk, fr[m]);
-                if (j == k + 1) vec[j] = xs[m]; /* the next column's head needs it */
-              }
-            }
-          }
-          __syncwarp();
-          ck += (size_t)(d - k);
+        {
+          double cur[RM], nx1[RM];
+          int off = 0, off1 = d - 1;
+          warp_load_col<RM>(cur, Lg + lane, off, 0, lane, d);
+          warp_load_col<RM>(nx1, Lg + lane, off1, 1 < d ? 1 : 0x7fff, lane, d);
+          warp_shaper_group<RM, 0>(Lg + lane, off, off1, cur, nx1, scale, lane, d, xs, fr);
         }
         /* |L|_F: slot l = rows l, l+32, ... in order; halving tree over the 32 slots */
         double slot = 0.0;
