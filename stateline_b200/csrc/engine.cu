@@ -9,7 +9,7 @@
 // Round r (0-based) makes the chain length r+2; a swap sweep happens when (r+2) % swapInterval == 0 and
 // an adapt point follows the round with (r+2) % adaptInterval == 0.  step_rounds() cuts the requested
 // rounds into launches that end at adapt points (or after maxRoundsPerLaunch rounds), each followed,
-// at an adapt point, by k_tier_adapt + k_ladder.  Cold-chain rows of a launch land in one of kSegments
+// at an adapt point, by k_tier_adapt.  Cold-chain rows of a launch land in one of kSegments
 // device segment buffers; with sink "host"/"csv" a second stream copies each finished segment into a
 // pinned host ring while the next launch runs.
 #include <cuda_runtime.h>
