@@ -82,16 +82,20 @@ __device__ __forceinline__ void gemv_block(const double* Lc, const double* zs, i
 }
 
 /* Columns K0..K0+KB-1 of ProposalShaper::update's rank-1 sweep (src/infer/adaptive.cpp:184-197).
- * xs (the scaled jump) and fr (row sums of squares) live in shared memory, one column per staged chain:
- * xs[j*xst], fr[j*fst].  They are indexed by the rolled column counter k there, which a register array
- * cannot be, and phase B then needs few enough registers for 12 warps per SM. */
+ * xs (the scaled jump, then the running rank-1 vector) and fr (row sums of squares) are REGISTER arrays: rows are
+ * unrolled, and inside a column block the column index k is one of the KB static candidates K0..K1-1, so x_k and
+ * row k's sum are picked by warp-uniform selects -- no shared-memory round trip per element (it was two loads and
+ * two stores of the 19 instructions per element, on the MIO pipe the kernel is short of). */
 template <int D, int K0, int K1>
-__device__ __forceinline__ void shaper_col(int k, double* Lk, const double* col, double scale, double* xs, int xst, double* fr, int fst) {
+__device__ __forceinline__ void shaper_col(int k, double* Lk, const double* col, double scale, double* xs, double* fr) {
   const double eps = 1e-18;
-  const double xk = xs[k * xst];
+  double xk = xs[K0];
   double Lkk = col[K0];
 #pragma unroll
-  for (int j = K0 + 1; j < K1; ++j) Lkk = (j == k) ? col[j] : Lkk;
+  for (int j = K0 + 1; j < K1; ++j) {
+    xk = (j == k) ? xs[j] : xk;
+    Lkk = (j == k) ? col[j] : Lkk;
+  }
   Lkk = Lkk * scale;
   const double V = smax(eps, Lkk);
   const double rV = 1.0 / V;
@@ -100,22 +104,24 @@ __device__ __forceinline__ void shaper_col(int k, double* Lk, const double* col,
   const double s = div_by(xk, V, rV);
   const double rc = 1.0 / c;
   Lk[(k * (k + 1) / 2) * kLs] = r;
-  fr[k * fst] = fma(r, r, fr[k * fst]); /* the diagonal closes row k's sum */
+#pragma unroll
+  for (int j = K0; j < K1; ++j)
+    if (j == k) fr[j] = fma(r, r, fr[j]); /* the diagonal closes row k's sum */
 #pragma unroll
   for (int j = K0 + 1; j < D; ++j) {
     if (j >= K1 || j > k) { /* static for j >= K1, warp-uniform otherwise */
-      const double xj = xs[j * xst];
+      const double xj = xs[j];
       double Ljk = col[j] * scale;
       Ljk = div_by(Ljk + s * xj, c, rc);
       Lk[(j * (j + 1) / 2) * kLs] = Ljk;
-      xs[j * xst] = c * xj - s * Ljk;
-      fr[j * fst] = fma(Ljk, Ljk, fr[j * fst]);
+      xs[j] = c * xj - s * Ljk;
+      fr[j] = fma(Ljk, Ljk, fr[j]);
     }
   }
 }
 
 template <int D, int K0, int KB>
-__device__ __forceinline__ void shaper_block(double* Lc, double scale, double* xs, int xst, double* fr, int fst) {
+__device__ __forceinline__ void shaper_block(double* Lc, double scale, double* xs, double* fr) {
   constexpr int K1 = (K0 + KB < D) ? K0 + KB : D;
 #pragma unroll 1
   for (int k = K0; k < K1; k += 2) { /* two columns per trip; column k's stores never touch column k+1 */
@@ -128,31 +134,28 @@ __device__ __forceinline__ void shaper_block(double* Lc, double scale, double* x
 #pragma unroll
       for (int j = K0; j < D; ++j) col1[j] = SLGPU_LDL(Lk + (j * (j + 1) / 2 + 1) * kLs);
     }
-    shaper_col<D, K0, K1>(k, Lk, col0, scale, xs, xst, fr, fst);
-    if (two) shaper_col<D, K0, K1>(k + 1, Lk + kLs, col1, scale, xs, xst, fr, fst);
+    shaper_col<D, K0, K1>(k, Lk, col0, scale, xs, fr);
+    if (two) shaper_col<D, K0, K1>(k + 1, Lk + kLs, col1, scale, xs, fr);
   }
-  if constexpr (K1 < D) shaper_block<D, K1, KB>(Lc, scale, xs, xst, fr, fst);
+  if constexpr (K1 < D) shaper_block<D, K1, KB>(Lc, scale, xs, fr);
 }
 
 /* ProposalShaper::update (src/infer/adaptive.cpp:173-209), blocked column sweep; Lc[(r(r+1)/2+k)*ls].
- * On entry xs[j*xst] holds the accepted jump; fr[j*fst] is scratch. */
+ * jump[j*jst] holds the accepted jump. */
 template <int D>
-__device__ __forceinline__ double shaper_update_rolled(double* Lc, double* xs, int xst, double* fr, int fst, double count,
-                                                        double prop_norm) {
+__device__ __forceinline__ double shaper_update_rolled(double* Lc, const double* jump, int jst, double count, double prop_norm) {
   const double eps = 1e-18;
   const double sq = sqrt(count);
   const double rsq = 1.0 / sq;
   const double scale = sqrt((count - 1.0) / count);
+  double xs[D], f[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    xs[i * xst] = div_by(xs[i * xst], sq, rsq);
-    fr[i * fst] = 0.0;
+    xs[i] = div_by(jump[i * jst], sq, rsq);
+    f[i] = 0.0;
   }
-  shaper_block<D, 0, kColBlock>(Lc, scale, xs, xst, fr, fst);
+  shaper_block<D, 0, kColBlock>(Lc, scale, xs, f);
   /* |L|_F: slot l = row sum l (D <= 32), halving tree over 32 slots; slots >= D are +0 and are skipped */
-  double f[D];
-#pragma unroll
-  for (int j = 0; j < D; ++j) f[j] = fr[j * fst];
   int nlive = D;
 #pragma unroll
   for (int mm = 16; mm > 0; mm >>= 1) {
@@ -443,10 +446,9 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       const bool mine = (tid & 31) < per && slot < nacc;
 #endif
 #ifndef SLGPU_PHASEB_PAIR /* measured on config #3: one lane per staged chain 59.7 us per round, a lane pair 68.8 */
-      if (mine) { /* jump in s_jump[.][slot]; this thread's (dead) column of s_z is the row-sum scratch */
+      if (mine) { /* jump in s_jump[.][slot] */
         const int own = s_owner[slot];
-        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, blk, own), D * (D + 1) / 2), s_jump + slot, NT, s_z + tid, NT,
-                                             s_cnt[slot], p.prop_norm);
+        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, blk, own), D * (D + 1) / 2), s_jump + slot, NT, s_cnt[slot], p.prop_norm);
       }
 #else
       (void)mine;
