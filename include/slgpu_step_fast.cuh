@@ -281,7 +281,7 @@ __device__ __forceinline__ u32 thread_chain(const slgpu_step_params& p, u32 blk,
 template <int D, int NT>
 inline size_t fast_smem_bytes(unsigned n_temps) {
   const size_t nsb = (size_t)(NT / 32) * (32u / n_temps);
-  return ((size_t)3 * D * NT + (size_t)2 * D * nsb) * sizeof(double) + SLGPU_FAST_SMEM_PAD;
+  return ((size_t)2 * D * NT + (size_t)D * (NT + 1) + (size_t)2 * D * nsb) * sizeof(double) + SLGPU_FAST_SMEM_PAD;
 }
 
 template <class Lik, int D, int NT>
@@ -302,9 +302,10 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   extern __shared__ double s_dyn[];
   double* const s_jump = s_dyn;              /* staged accepted jumps, [i][slot] */
   double* const s_z = s_dyn + D * NT;        /* this round's normals, [k][thread] */
-  double* const s_x = s_dyn + 2 * D * NT;    /* current sample of every chain of the block, [i][thread] */
+  constexpr int NX = NT + 1;                 /* row stride of s_x: odd, so that a column (one chain, all i) is conflict-free too */
+  double* const s_x = s_dyn + 2 * D * NT;    /* current sample of every chain of the block, [i][thread], rows NX apart */
   const int nsb = (NT / 32) * m.spw;         /* stacks per block */
-  double* const s_epm = s_dyn + 3 * D * NT;  /* EPSRDiagnostic M, [i][stack of block] */
+  double* const s_epm = s_dyn + 2 * D * NT + D * NX;  /* EPSRDiagnostic M, [stack of block][i] */
   double* const s_eps = s_epm + D * nsb;     /* EPSRDiagnostic S */
   const int sb = (tid >> 5) * m.spw + m.sl;  /* this thread's stack within the block */
   __shared__ double s_cnt[NT];      /* shaper count (already incremented) of the staged chain */
@@ -330,12 +331,12 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   const Lik lik(p.payload);
   const double* Lc = l_base(p.L, c, D * (D + 1) / 2); /* rewritten by other threads in phase B: no __restrict__ */
 #pragma unroll
-  for (int i = 0; i < D; ++i) s_x[i * NT + tid] = p.x[(size_t)i * C + c];
+  for (int i = 0; i < D; ++i) s_x[i * NX + tid] = p.x[(size_t)i * C + c];
   if (active && m.t == 0) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      s_epm[i * nsb + sb] = p.ep_m[(size_t)i * p.n_stacks + m.s];
-      s_eps[i * nsb + sb] = p.ep_s[(size_t)i * p.n_stacks + m.s];
+      s_epm[sb * D + i] = p.ep_m[(size_t)i * p.n_stacks + m.s];
+      s_eps[sb * D + i] = p.ep_s[(size_t)i * p.n_stacks + m.s];
     }
   }
   double Ps[9];
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       /* GaussianProposal::propose (sampler.cpp:79-88): a_i = sum_{k<=i} fma(N_ik, z_k, .), k ascending */
       gemv_block<D, 0, kColBlock>(Lc, s_z + tid, NT, nscale, fresh, s_n0, a);
 #pragma unroll
-      for (int i = 0; i < D; ++i) a[i] = bounce1(s_x[i * NT + tid] + a[i] * sigma, s_mn[i], s_mx[i], s_rd[i]);
+      for (int i = 0; i < D; ++i) a[i] = bounce1(s_x[i * NX + tid] + a[i] * sigma, s_mn[i], s_mx[i], s_rd[i]);
       /* energy = sum over job types in order (sampler.cpp:148-150) */
       double e_new = 0.0;
       if constexpr (StaticJobs<Lik, D>::value > 0) {
@@ -405,8 +406,8 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           const double nx = a[i];
-          s_jump[i * NT + slot] = nx - s_x[i * NT + tid]; /* the accepted jump (sampler.cpp:166) */
-          s_x[i * NT + tid] = nx;
+          s_jump[i * NT + slot] = nx - s_x[i * NX + tid]; /* the accepted jump (sampler.cpp:166) */
+          s_x[i * NX + tid] = nx;
         }
         s_cnt[slot] = sh_count;
         s_owner[slot] = (unsigned short)tid;
@@ -507,10 +508,10 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
         const int src_tid = (tid & ~31) + ((m.base + my_src) & 31);
         double g[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) g[i] = s_x[i * NT + src_tid];
+        for (int i = 0; i < D; ++i) g[i] = s_x[i * NX + src_tid];
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < D; ++i) s_x[i * NT + tid] = g[i];
+        for (int i = 0; i < D; ++i) s_x[i * NX + tid] = g[i];
         __syncwarp();
       }
       energy = new_e;
@@ -556,9 +557,9 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
         const int sl = task / D, i = task - sl * D;
         const u32 sc = s0 + (u32)sl;
         if (sc < p.n_stacks) {
-          const int o = i * nsb + (tid >> 5) * m.spw + sl;
+          const int o = ((tid >> 5) * m.spw + sl) * D + i; /* [stack][i]: consecutive lanes, consecutive words */
           const double mo = s_epm[o];
-          const double xi = s_x[i * NT + (tid & ~31) + sl * T];
+          const double xi = s_x[i * NX + (tid & ~31) + sl * T];
           const double newM = mo + div_by(xi - mo, nn, rnn);
           s_eps[o] = s_eps[o] + (xi - mo) * (xi - newM);
           s_epm[o] = newM;
@@ -571,12 +572,12 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 
   if (active) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) p.x[(size_t)i * C + c] = s_x[i * NT + tid];
+    for (int i = 0; i < D; ++i) p.x[(size_t)i * C + c] = s_x[i * NX + tid];
     if (m.t == 0) {
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        p.ep_m[(size_t)i * p.n_stacks + m.s] = s_epm[i * nsb + sb];
-        p.ep_s[(size_t)i * p.n_stacks + m.s] = s_eps[i * nsb + sb];
+        p.ep_m[(size_t)i * p.n_stacks + m.s] = s_epm[sb * D + i];
+        p.ep_s[(size_t)i * p.n_stacks + m.s] = s_eps[sb * D + i];
       }
     }
     p.energy[c] = energy;
