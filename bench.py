@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
     value = tot_steps / tot_s
     sample = "%d stacks x %d temps of config #3, %d rounds per step, server + %d worker threads (oracle port of src/infer + FIFO job farm with %%f wire text)" % (
         stacks, w["T"], rounds_per_step, n_workers)
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -180,7 +180,28 @@ def bench_config(T, d, J, S):
             "l2": "chain state per GPU (~140 MB, L factors 110 MB) exceeds the 126 MB L2 and every step rewrites it: no explicit flush"}
 
 
+_json_out = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints its version line on
+    stdout when NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the run and the JSON line goes
+    to a private copy of the original stdout."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _json_out or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -353,7 +374,7 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "chain-steps/s", "cores": nwk + 1, "kind": "port", "sample": sample}
         vi, si = cpu_baseline(0, 4.0)
         out["cpu_baseline"]["inline_1_thread"] = {"value": vi, "sample": si}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     if dist:
         dist.destroy_process_group()
 
