@@ -49,3 +49,14 @@ def test_algorithmic_bytes_closed_form():
     # (d + d(d+1)/2 + 6) doubles in and out once per launch of K rounds + (d+5) doubles per cold row
     assert bench.algorithmic_bytes_per_chain_step(20, 8, 10) == (20 + 210 + 6) * 16 / 10 + 25 * 8 / 8
     assert round(bench.algorithmic_bytes_per_chain_step(20, 8, 10)) == 403
+
+
+def test_stdout_carries_only_the_json_line():
+    """Native libraries print on fd 1 (NCCL's version line under NCCL_DEBUG): after bench._claim_stdout() such
+    writes go to stderr and only bench._emit() reaches the real stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._claim_stdout(); "
+            "os.write(1, b'NCCL version 0.0\\n'); print('python-level noise'); bench._emit('{\"ok\": 1}')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, timeout=120)
+    assert r.returncode == 0
+    assert r.stdout.decode().splitlines() == ['{"ok": 1}']
+    assert b"NCCL version 0.0" in r.stderr and b"python-level noise" in r.stderr
