@@ -44,15 +44,37 @@ def build(force=False):
     return _LIB_PATH
 
 
+_LIBM_PATH = os.path.join(_HERE, "libsl_oracle_libm.so")
 _lib = None
+_lib_libm = None
 
 
-def lib():
-    global _lib
+def build_libm(force=False):
+    """The oracle with glibc exp/log (-DSLO_LIBM): compared bit for bit with oracle/_ref (oracle/ref.py)."""
+    src = os.path.join(_HERE, "sl_oracle.cpp")
+    hdr = os.path.join(_HERE, "sl_oracle.h")
+    if (not force and os.path.exists(_LIBM_PATH)
+            and os.path.getmtime(_LIBM_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return _LIBM_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libsl_oracle_libm.so"], stdout=subprocess.DEVNULL)
+    return _LIBM_PATH
+
+
+def lib(libm=False):
+    global _lib, _lib_libm
+    if libm:
+        if _lib_libm is None:
+            build_libm()
+            _lib_libm = _declare(C.CDLL(_LIBM_PATH))
+        return _lib_libm
     if _lib is not None:
         return _lib
     build()
-    L = C.CDLL(_LIB_PATH)
+    _lib = _declare(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _declare(L):
     L.slo_create.restype = C.c_void_p
     L.slo_create.argtypes = [C.POINTER(SloConfig)]
     L.slo_destroy.argtypes = [C.c_void_p]
@@ -97,7 +119,6 @@ def lib():
     L.slo_target_eval.argtypes = [C.c_int32, _dp, C.c_uint32, C.c_uint32, C.c_uint32, _dp]
     L.slo_time_server_workers.restype = C.c_double
     L.slo_time_server_workers.argtypes = [C.POINTER(SloConfig), C.c_uint32, C.c_uint64, _u64p]
-    _lib = L
     return L
 
 
@@ -138,15 +159,16 @@ def make_config(S, T, J, swap_interval, opt_accept, opt_swap, mn, mx, target, ta
 class Sampler:
     """Thin object wrapper over slo_sampler."""
 
-    def __init__(self, **kw):
+    def __init__(self, libm=False, **kw):
+        self._L = lib(libm)
         self.cfg, self._keep = make_config(**kw)
         self.S, self.T, self.d = self.cfg.n_stacks, self.cfg.n_temps, self.cfg.n_dims
         self.C = self.S * self.T
-        self.h = lib().slo_create(C.byref(self.cfg))
+        self.h = self._L.slo_create(C.byref(self.cfg))
 
     def close(self):
         if self.h:
-            lib().slo_destroy(self.h)
+            self._L.slo_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -155,70 +177,70 @@ class Sampler:
     def set_replay(self, z, u_mh, u_swap, x_init):
         self._replay = [_f64(z), _f64(u_mh), _f64(u_swap), _f64(x_init)]
         n_rounds = self._replay[1].shape[0]
-        lib().slo_set_replay(self.h, *[_p(a) for a in self._replay], n_rounds)
+        self._L.slo_set_replay(self.h, *[_p(a) for a in self._replay], n_rounds)
 
     def init_chains(self):
-        lib().slo_init_chains(self.h)
+        self._L.slo_init_chains(self.h)
 
     def run_rounds(self, n):
-        lib().slo_run_rounds(self.h, n)
+        self._L.slo_run_rounds(self.h, n)
 
     def flush(self):
-        lib().slo_flush(self.h)
+        self._L.slo_flush(self.h)
 
     def last_rows(self):
         out = np.empty((self.C, self.d + 5))
-        lib().slo_get_last_rows(self.h, _p(out))
+        self._L.slo_get_last_rows(self.h, _p(out))
         return out
 
     def sigma_beta(self):
         s = np.empty(self.C)
         b = np.empty(self.C)
-        lib().slo_get_sigma_beta(self.h, _p(s), _p(b))
+        self._L.slo_get_sigma_beta(self.h, _p(s), _p(b))
         return s, b
 
     def shaper(self, chain):
         L = np.empty((self.d, self.d))
         N = np.empty((self.d, self.d))
         cnt = np.empty(1)
-        lib().slo_get_shaper(self.h, chain, _p(L), _p(N), _p(cnt))
+        self._L.slo_get_shaper(self.h, chain, _p(L), _p(N), _p(cnt))
         return L, N, float(cnt[0])
 
     def models(self, which):
-        n = lib().slo_n_models(self.h)
+        n = self._L.slo_n_models(self.h)
         xx = np.empty((n, 9))
         xy = np.empty((n, 3))
         w = np.empty((n, 3))
         cnt = np.empty(n)
-        lib().slo_get_models(self.h, which, _p(xx), _p(xy), _p(w), _p(cnt))
+        self._L.slo_get_models(self.h, which, _p(xx), _p(xy), _p(w), _p(cnt))
         return xx, xy, w, cnt
 
     def counters(self):
         arrs = [np.empty(self.C, dtype=np.uint64) for _ in range(4)]
         mine = np.empty(self.C)
-        lib().slo_get_counters(self.h, *[a.ctypes.data_as(_u64p) for a in arrs], _p(mine))
+        self._L.slo_get_counters(self.h, *[a.ctypes.data_as(_u64p) for a in arrs], _p(mine))
         return dict(length=arrs[0], accepts=arrs[1], swaps=arrs[2], swap_attempts=arrs[3], min_energy=mine)
 
     def logger(self):
         cur, ar, sr = np.empty(self.C), np.empty(self.C), np.empty(self.C)
-        lib().slo_get_logger(self.h, _p(cur), _p(ar), _p(sr))
+        self._L.slo_get_logger(self.h, _p(cur), _p(ar), _p(sr))
         return cur, ar, sr
 
     def format_table(self):
-        n = lib().slo_format_table(self.h, None, 0)
+        n = self._L.slo_format_table(self.h, None, 0)
         buf = C.create_string_buffer(n + 1)
-        lib().slo_format_table(self.h, buf, n + 1)
+        self._L.slo_format_table(self.h, buf, n + 1)
         return buf.value.decode()
 
     def cold_rows(self, stack):
-        n = lib().slo_cold_rows(self.h, stack, None, 0)
+        n = self._L.slo_cold_rows(self.h, stack, None, 0)
         out = np.empty((n, self.d + 5))
-        lib().slo_cold_rows(self.h, stack, _p(out), n)
+        self._L.slo_cold_rows(self.h, stack, _p(out), n)
         return out
 
     def rhat(self):
         out = np.empty(self.d)
-        lib().slo_rhat(self.h, _p(out))
+        self._L.slo_rhat(self.h, _p(out))
         return out
 
 

@@ -33,6 +33,16 @@
 #include <thread>
 #include <vector>
 
+#ifdef SLO_LIBM
+/* libsl_oracle_libm.so (oracle/Makefile): exp and log from glibc, exactly as the reference calls them
+ * (chainarray.cpp:41,64; sampler.cpp:160; adaptive.cpp:116,130,136), instead of the slgpu_math.h kernels the
+ * device shares.  Only tests/test_ref_pin.py uses this build: it must agree BIT FOR BIT with the reference's own
+ * sources (oracle/_ref); the default build is then tied to it within 1 ulp per call (tests/test_math.py) and to the
+ * GPU bit for bit. */
+#define slm_exp(x) std::exp(x)
+#define slm_log(x) std::log(x)
+#endif
+
 namespace {
 
 using u32 = uint32_t;

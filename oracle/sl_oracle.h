@@ -8,14 +8,19 @@
  * load it.  The product path (stateline_b200/, include/) never includes, links or
  * executes anything under oracle/.
  *
- * Parity pin status: the reference cannot be compiled in this image (Eigen and
- * zmq.h are absent), so the oracle is pinned by
+ * Parity pin status: PINNED AGAINST THE REFERENCE'S OWN CODE.  The reference's build (cmake + Eigen + ZeroMQ) does
+ * not run in this image, but its src/infer/{sampler,chainarray,adaptive}.cpp and src/db/db.cpp compile UNMODIFIED
+ * against the stand-in Eigen / zmq headers of oracle/ref_shim into oracle/_ref/libsl_ref.so (oracle/Makefile.ref,
+ * oracle/ref_harness.cpp).  Fed the variates the reference itself drew, this oracle (sequential schedule, glibc
+ * exp/log build libsl_oracle_libm.so) reproduces the reference bit for bit: chain rows, sigma/beta, tier models,
+ * proposal shapes, cold rows, CSV text, flush -- tests/test_ref_pin.py, live and from the committed fixtures
+ * tests/golden/ref_*.json.  What stays unpinned by a third party: the three places where the reference delegates
+ * to Eigen (GEMV summation order, Frobenius norm order, the 3x3 colPivHouseholderQr), where shim and oracle share
+ * one canonical order.  Further pins:
  *   - the reference's own EPSR known answers (src/test/diagnostics.cpp:34,53,78),
  *   - the swap-formula case of src/test/chainarray.cpp:104-125,
- *   - hand-derived KATs listed in tests/golden/README.md,
+ *   - hand-derived KATs in tests/test_oracle.py,
  *   - the README's soft statistics (README.md:421-435).
- * Sampler / adapter / shaper arithmetic has NO golden vectors in the reference
- * ("parity unpinned" for those rows).
  */
 #ifndef SL_ORACLE_H
 #define SL_ORACLE_H

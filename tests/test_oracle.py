@@ -152,7 +152,7 @@ def test_csv_row_format():
 
 
 # ---- golden fixture: oracle output recorded by tests/golden/make_golden.py -----------------------------
-GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".json"))
+GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.startswith("oracle_") and f.endswith(".json"))
 
 
 @pytest.mark.parametrize("name", GOLDEN)

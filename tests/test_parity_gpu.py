@@ -107,7 +107,7 @@ def test_step_kernel_variants_agree(monkeypatch):
             assert np.array_equal(a, b)
 
 
-GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".json"))
+GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.startswith("oracle_") and f.endswith(".json"))
 
 
 @pytest.mark.parametrize("name", GOLDEN)
