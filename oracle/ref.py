@@ -80,6 +80,9 @@ def lib():
     L.slref_cold_rows.argtypes = [C.c_void_p, C.c_uint32, _dp, C.c_uint64]
     L.slref_length.restype = C.c_uint32
     L.slref_length.argtypes = [C.c_void_p, C.c_uint32]
+    L.slref_step_print.restype = C.c_size_t
+    L.slref_step_print.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.slref_get_logger.argtypes = [C.c_void_p] + [_dp] * 7
     L.slref_bouncy_bounds.argtypes = [_dp, _dp, _dp, C.c_uint32, _dp]
     _lib = L
     return L
@@ -139,6 +142,20 @@ class RefRun:
     def run_rounds(self, n):
         """n canonical rounds = n * S*T calls of Sampler::step()."""
         self._L.slref_step(self.h, n * self.C)
+
+    def step_print(self):
+        """One more Sampler::step() on which TableLogger prints (logging.cpp:50-87); returns the captured text."""
+        buf = C.create_string_buffer(1 << 20)
+        self._L.slref_step_print(self.h, buf, len(buf))
+        return buf.value.decode()
+
+    def logger(self):
+        """TableLogger's counters and EPSRDiagnostic::rHat()."""
+        a = [np.empty(self.C) for _ in range(6)]
+        rhat = np.empty(self.d)
+        self._L.slref_get_logger(self.h, *[_p(x) for x in a], _p(rhat))
+        return dict(length=a[0], min_energy=a[1], cur_energy=a[2], accepts=a[3], swaps=a[4], swap_attempts=a[5],
+                    rhat=rhat)
 
     def flush(self):
         self._L.slref_flush(self.h)

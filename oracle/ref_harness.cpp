@@ -8,6 +8,8 @@
  *                           propose/unlock/flush), src/infer/chainarray.cpp (acceptProposal, acceptSwap,
  *                           ChainArray::append/swap/flushToDisk/...), src/infer/adaptive.cpp
  *                           (RegressionAdapter, ProposalShaper), src/db/db.cpp (CSV writer, row format),
+ *                           src/infer/logging.cpp (TableLogger: counters and the printed table),
+ *                           src/infer/diagnostics.cpp (EPSRDiagnostic),
  *                           and every header they include except Eigen and zmq.hpp.
  *   stand-ins (this repo) : Eigen  -> oracle/ref_shim/Eigen/Core (GEMV, norm and the 3x3 QR solve follow the
  *                           oracle's canonical orders; see its header);
@@ -20,6 +22,8 @@
  *                           the init loop of runSampler (src/app/serverwrapper.cpp:48-87; that file drags in
  *                           the delegator, the HTTP API and the logger) is restated in slref_create(), with
  *                           the caller's pre-bounce start points instead of VectorXd::Random;
+ *                           ApiResources::set (src/app/api.cpp:13-18, the HTTP side of that file is not built):
+ *                           only so that logging.cpp links; TableLogger::updateApi is never called;
  *                           the three std::mt19937 are seeded from the caller's seed instead of
  *                           std::random_device, and every variate is recorded (oracle/ref_shim/ref_prelude.h).
  */
@@ -58,6 +62,7 @@
 #include "infer/sampler.hpp"
 #include "infer/adaptive.hpp"
 #include "infer/chainarray.hpp"
+#include "infer/logging.hpp"
 #undef private
 
 INITIALIZE_EASYLOGGINGPP
@@ -188,6 +193,10 @@ std::pair<uint, std::vector<double>> Requester::retrieve() {
 }  // namespace comms
 }  // namespace stateline
 
+namespace stateline {
+void ApiResources::set(const std::string& name, json data) { resources_[name] = data.dump(); }
+}  // namespace stateline
+
 /* ---- the run object ---- */
 struct slref_run {
   slref::Harness h;
@@ -198,6 +207,8 @@ struct slref_run {
   std::unique_ptr<stateline::mcmc::ChainArray> chains;
   std::unique_ptr<stateline::comms::Requester> requester;
   std::unique_ptr<stateline::mcmc::Sampler> sampler;
+  std::unique_ptr<stateline::mcmc::TableLogger> logger;
+  std::string lastTable;
   /* what runSampler's loop sees: the (id, state) pairs step() returns for cold chains, in order */
   std::vector<std::vector<double>> cold; /* [stack] -> rows of d+5 */
   uint64_t steps = 0;
@@ -280,6 +291,8 @@ slref_run* slref_create(const slref_config* cfg, const double* x_init) {
   h.running = true;
   r->sampler.reset(new mcmc::Sampler(*r->requester, jobTypes, *r->chains, *r->proposal, *r->sigmaAdapter,
                                      *r->betaAdapter, cfg->swap_interval));
+  /* serverwrapper.cpp:95; the refresh period is "never": slref_step_print forces the print */
+  r->logger.reset(new mcmc::TableLogger(h.S, h.T, h.d, 0x7fffffff));
   return r;
 }
 
@@ -290,8 +303,42 @@ void slref_step(slref_run* r, uint64_t n_steps) {
   for (uint64_t i = 0; i < n_steps; ++i) {
     std::tie(id, state) = r->sampler->step();
     if (id % r->h.T == 0) push_row(r->cold[id / r->h.T], state);
+    /* serverwrapper.cpp:124-126 */
+    r->logger->update(id, state, r->sigmaAdapter->values(), r->sigmaAdapter->rates(), r->betaAdapter->values(),
+                      r->betaAdapter->rates());
     r->steps++;
   }
+}
+
+/* One more step, on which TableLogger::update finds its refresh period expired and prints the table and the
+ * convergence line (logging.cpp:50-87) to std::cout, captured here.  Returns the text length. */
+size_t slref_step_print(slref_run* r, char* out, size_t cap) {
+  std::ostringstream capture;
+  std::streambuf* old = std::cout.rdbuf(capture.rdbuf());
+  r->logger->msRefresh_ = 0;
+  r->logger->lastPrintTime_ = std::chrono::steady_clock::time_point();
+  slref_step(r, 1);
+  r->logger->msRefresh_ = 0x7fffffff;
+  std::cout.rdbuf(old);
+  r->lastTable = capture.str();
+  if (out && cap) {
+    const size_t n = std::min(cap - 1, r->lastTable.size());
+    std::memcpy(out, r->lastTable.data(), n);
+    out[n] = 0;
+  }
+  return r->lastTable.size();
+}
+
+/* TableLogger's counters and EPSR (logging.cpp:29-48, diagnostics.cpp:49-71) */
+void slref_get_logger(const slref_run* r, double* length, double* min_energy, double* cur_energy, double* accepts,
+                      double* swaps, double* swap_attempts, double* rhat) {
+  const auto& lg = *r->logger;
+  for (uint32_t c = 0; c < r->h.C; ++c) {
+    length[c] = lg.lengths_[c]; min_energy[c] = lg.minEnergies_[c]; cur_energy[c] = lg.energies_[c];
+    accepts[c] = lg.nAcceptsGlobal_[c]; swaps[c] = lg.nSwapsGlobal_[c]; swap_attempts[c] = lg.nSwapAttemptsGlobal_[c];
+  }
+  Eigen::ArrayXd rh = lg.diagnostic_.rHat();
+  for (uint32_t i = 0; i < r->h.d; ++i) rhat[i] = rh(i);
 }
 
 void slref_flush(slref_run* r) { r->sampler->flush(); }

@@ -999,10 +999,14 @@ size_t slo_format_table(const slo_sampler* o, char* out, size_t cap) {
     s += cell;
     num(o->lgMinE[i]);
     num(o->lgCurE[i]);
-    num(o->sigma_[i]);
+    /* the Sigma and Beta columns are the ADAPTERS' values() (serverwrapper.cpp:124-126), not ChainArray's: after a
+     * cascade computeBetaStack has already rewritten values_[2..T-1] while those chains keep their old beta until
+     * the next cascade reaches them (sampler.cpp:179-186), so the table shows the ladder to come.  Found by running
+     * the reference's own TableLogger (tests/test_ref_pin.py); in the batched schedule both are always equal. */
+    num(o->sigAd.values[i]);
     num(o->sigAd.rates[i]);
     num(o->lgAccepts[i] / (double)o->lgLength[i]);
-    num(o->beta_[i]);
+    num(o->betaAd.values[i]);
     num(o->betaAd.rates[i]);
     num(o->lgSwaps[i] / (double)o->lgSwapAttempts[i]);
     s += '\n';

@@ -6,7 +6,7 @@ unmodified from /root/reference, see oracle/Makefile.ref and oracle/ref_harness.
 Each fixture records one seeded reference run: the configuration, the start points, every variate the reference
 drew (its own std::mt19937 / normal_distribution / uniform_real_distribution, seed pinned), and what the
 reference computed from them: the last row of every chain, ChainArray's sigma/beta, the tier models, one proposal
-shape and the text of the CSV files it wrote.  tests/test_ref_pin.py replays the draws through the oracle
+shape, the TableLogger's counters, R-hat and printed table, and the text of the CSV files it wrote.  tests/test_ref_pin.py replays the draws through the oracle
 (sequential schedule, glibc exp/log) and requires the same bits; the fixtures travel, the reference does not.
 Floats are stored as hex so the JSON round trip is exact.
 """
@@ -64,8 +64,11 @@ def run_case(c):
     out = tempfile.mkdtemp(prefix="slref_")
     r = R.RefRun(S, T, c["J"], c["swap_interval"], c["opt_accept"], c["opt_swap"], c["mn"], c["mx"], c["target"],
                  x_init, out, target_params=c["target_params"], seed=c["seed"], wire=c["wire"], max_rounds=n + 2)
-    r.run_rounds(n)
+    r.run_rounds(n - 1)
+    r._L.slref_step(r.h, C - 1)
+    table = r.step_print()  # the last step of round n-1 is one on which TableLogger prints (logging.cpp:50-87)
     assert r.unattributed() == 0
+    lg = r.logger()
     fx = dict(
         generator="tests/golden/make_ref_golden.py (reference sources: src/infer/{sampler,chainarray,adaptive}.cpp, src/db/db.cpp)",
         config=dict(S=S, T=T, J=c["J"], swap_interval=c["swap_interval"], opt_accept=c["opt_accept"],
@@ -73,7 +76,8 @@ def run_case(c):
                     target=int(c["target"]),
                     target_params=None if c["target_params"] is None else hexa(c["target_params"]),
                     seed=c["seed"], wire=c["wire"], rounds=n),
-        x_init=hexa(x_init), last_rows=hexa(r.last_rows()),
+        x_init=hexa(x_init), last_rows=hexa(r.last_rows()), table=table, rhat=hexa(lg["rhat"]),
+        logger={k: hexa(lg[k]) for k in ("length", "min_energy", "cur_energy", "accepts", "swaps", "swap_attempts")},
     )
     s, b = r.sigma_beta()
     fx["sigma"], fx["beta"] = hexa(s), hexa(b)
