@@ -99,6 +99,77 @@ def cpu_baseline(n_workers, budget_s, stacks=64):
         w["S"], w["T"], rounds, steps, "server + %d worker threads, FIFO job farm, %%f wire text" % n_workers if n_workers else "inline, 1 thread")
 
 
+class ReferencePool:
+    """N independent reference samplers, one process per host core (tools/ref_worker.py): the reference's own
+    src/infer object code (oracle/_ref) with an in-process worker.  step(rounds) runs `rounds` rounds in every process
+    at once and returns (wall seconds, chain steps)."""
+
+    def __init__(self, n_procs, stacks_per_proc):
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        self.procs = [subprocess.Popen([sys.executable, "-u", os.path.join(here, "tools", "ref_worker.py"), str(i),
+                                        str(stacks_per_proc), WORKLOAD], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                       text=True, bufsize=1) for i in range(n_procs)]
+        self.chains = 0
+        for p in self.procs:
+            line = p.stdout.readline().split()
+            if not line or line[0] != "ready":
+                self.close()
+                raise RuntimeError("reference worker did not start")
+            self.chains += int(line[1])
+
+    def step(self, rounds):
+        t0 = time.perf_counter()
+        for p in self.procs:
+            p.stdin.write("%d\n" % rounds)
+            p.stdin.flush()
+        for p in self.procs:
+            float(p.stdout.readline())
+        return time.perf_counter() - t0, self.chains * rounds
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write("0\n")
+                p.stdin.flush()
+                p.stdin.close()
+            except Exception:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=30)
+            except Exception:
+                p.kill()
+
+
+def reference_available():
+    """oracle/_ref (the reference's own sources, built where /root/reference exists; the built file travels)."""
+    try:
+        from oracle import ref as R
+        return R.build() is not None
+    except Exception:
+        return False
+
+
+REF_STACKS_PER_PROC = 8
+REF_SAMPLE = ("%d independent stateline servers (one per host core), %d stacks x %d temps of config #3 each, %d rounds%s: "
+              "the reference's own src/infer + src/db object code (oracle/_ref), in-process worker instead of ZeroMQ")
+
+
+def cpu_baseline_reference(budget_s):
+    """cpu_baseline from oracle/_ref on all host cores, about budget_s seconds."""
+    cores = os.cpu_count() or 1
+    pool = ReferencePool(cores, REF_STACKS_PER_PROC)
+    try:
+        pool.step(20)  # warm-up: adaptation settles, caches fill
+        secs, _ = pool.step(20)
+        rounds = max(20, int(20 * budget_s / max(secs, 1e-6)))
+        secs, steps = pool.step(rounds)
+    finally:
+        pool.close()
+    return steps / secs, cores, REF_SAMPLE % (cores, REF_STACKS_PER_PROC, 8, rounds, "")
+
+
 def ess_geyer(x):
     """Effective sample size of a 1-D series by Geyer's initial positive sequence."""
     import numpy as np
@@ -137,9 +208,44 @@ def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000):
     return float(np.mean(per_stack)) / rounds
 
 
+def run_reference_ref(args):
+    """--impl reference through oracle/_ref: the reference's own object code on every host core."""
+    from stateline_b200 import configs
+    w = configs.workload(WORKLOAD, S=REF_STACKS_PER_PROC)
+    cores = os.cpu_count() or 1
+    pool = ReferencePool(cores, REF_STACKS_PER_PROC)
+    try:
+        secs, _ = pool.step(10)
+        rounds_per_step = max(1, int(10 * args.ref_seconds / max(secs * (args.steps + args.warmup), 1e-9)))
+        for _ in range(args.warmup):
+            pool.step(rounds_per_step)
+        tot_s, tot_steps = 0.0, 0
+        for _ in range(args.steps):
+            s_, n_ = pool.step(rounds_per_step)
+            tot_s += s_
+            tot_steps += n_
+    finally:
+        pool.close()
+    value = tot_steps / tot_s
+    sample = REF_SAMPLE % (cores, REF_STACKS_PER_PROC, w["T"], rounds_per_step, " per step")
+    _emit(json.dumps({
+        "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(w["T"], w["d"], w["J"], 8192),
+        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if reference_available() and not args.ref_port:
+        try:
+            return run_reference_ref(args)
+        except Exception as e:  # fall back to the port rather than lose the arm
+            sys.stderr.write("oracle/_ref arm failed (%r): falling back to the oracle port\n" % (e,))
     cores = os.cpu_count() or 1
     n_workers = max(1, cores - 1)
     from oracle import oracle as O
@@ -211,6 +317,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port (server + N worker threads) even when oracle/_ref exists")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU seconds the whole run is sized for")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -370,10 +477,24 @@ def main():
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         nwk = max(1, cores - 1)
-        v, sample = cpu_baseline(nwk, args.cpu_budget)
-        out["cpu_baseline"] = {"value": v, "unit": "chain-steps/s", "cores": nwk + 1, "kind": "port", "sample": sample}
+        base = None
+        if reference_available():
+            # the reference's own object code (oracle/_ref), one independent server per host core
+            try:
+                v, ncores, sample = cpu_baseline_reference(args.cpu_budget)
+                base = {"value": v, "unit": "chain-steps/s", "cores": ncores, "kind": "reference", "sample": sample}
+            except Exception as e:
+                sys.stderr.write("oracle/_ref baseline failed (%r): using the oracle port\n" % (e,))
+        # the oracle port in the reference's deployment shape: one server, N worker threads, FIFO job farm, %f wire text
+        vp, sp = cpu_baseline(nwk, args.cpu_budget if base is None else 6.0)
+        port = {"value": vp, "cores": nwk + 1, "kind": "port", "sample": sp}
+        if base is None:
+            base = dict(port, unit="chain-steps/s")
+        else:
+            base["port_server_workers"] = port
+        out["cpu_baseline"] = base
         vi, si = cpu_baseline(0, 4.0)
-        out["cpu_baseline"]["inline_1_thread"] = {"value": vi, "sample": si}
+        out["cpu_baseline"]["inline_1_thread"] = {"value": vi, "kind": "port", "sample": si}
     _emit(json.dumps(out))
     if dist:
         dist.destroy_process_group()

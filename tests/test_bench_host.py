@@ -19,10 +19,32 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "chain_steps_per_sec" and line["unit"] == "chain-steps/s"
     assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1 and line["higher_is_better"] is True
     assert line["value"] > 0 and line["ms_per_step"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    # oracle/_ref (the reference's own object code) when it is built or buildable here, else the oracle port
+    assert line["cpu_baseline"]["kind"] == ("reference" if bench.reference_available() else "port")
+    assert line["cpu_baseline"]["value"] == line["value"]
     assert line["cpu_baseline"]["cores"] >= 1 and "config #3" in line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("config3") and line["dtype"] == "f64"
+
+
+def test_reference_arm_port_fallback_keeps_the_contract():
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-port",
+                                   "--steps", "1", "--warmup", "1", "--ref-seconds", "2"], cwd=ROOT, timeout=300)
+    line = json.loads(out.decode().strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert "server +" in line["cpu_baseline"]["sample"]
+
+
+def test_reference_pool_counts_chain_steps():
+    if not bench.reference_available():
+        import pytest
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    pool = bench.ReferencePool(2, 3)
+    try:
+        secs, steps = pool.step(5)
+    finally:
+        pool.close()
+    assert steps == 2 * 3 * 8 * 5 and secs > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
