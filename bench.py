@@ -474,7 +474,7 @@ def main():
         eps = ess_per_cold_sample(local_rank)
         out["ess"] = {"ess_per_cold_sample": eps, "ess_per_sec": eps * value / T,
                       "estimator": "Geyer initial positive sequence, min over dims, mean over 128 stacks of a side run"}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU legs run at N=1 only
         cores = os.cpu_count() or 1
         nwk = max(1, cores - 1)
         base = None
