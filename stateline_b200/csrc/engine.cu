@@ -73,6 +73,7 @@ struct Settings {
   uint32_t adaptInterval = 0, maxRoundsPerLaunch = 64;
   uint64_t hostRingRounds = 0;
   bool overwrite = false;
+  bool sequential = false;   // "gpu": {"schedule": "sequential"}: the reference's own update order (validation mode)
   bool windowRates = false;  // keep the adapters' windowed accept / swap rates (the AcptRt / SwapRt columns of the table logger)
   uint32_t csvThreads = 0;  // csv sink: formatter threads (0 = one per host core, at most 16)
   bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
@@ -126,6 +127,7 @@ struct slgpu_engine {
   std::vector<StateBuf> state;         // everything a resumed run needs (slgpu_save_state / slgpu_load_state)
   slgpu_step_params P{};
   double *d_models = nullptr, *d_sig_w = nullptr, *d_ladder = nullptr, *d_sums = nullptr;
+  double* d_beta_values = nullptr;  // sequential schedule: RegressionAdapter::values_ of the beta adapter, [C]
   void* d_payload = nullptr;
   unsigned int* d_ticket = nullptr;    // last-block ticket of k_tier_adapt
   unsigned char* d_round_flags = nullptr;  // windowRates: [seg_rounds][C] per-round accept / swap flags of a launch
@@ -221,6 +223,12 @@ Settings parse_settings(const char* text) {
     if (g->find("maxRoundsPerLaunch")) s.maxRoundsPerLaunch = (uint32_t)need_uint(*g, "maxRoundsPerLaunch");
     if (g->find("hostRingRounds")) s.hostRingRounds = need_uint(*g, "hostRingRounds");
     if (g->find("overwrite")) s.overwrite = need(*g, "overwrite", slgpu_json::Value::Bool).b;
+    if (g->find("schedule")) {
+      const std::string& k = need(*g, "schedule", slgpu_json::Value::String).str;
+      if (k == "batched") s.sequential = false;
+      else if (k == "sequential") s.sequential = true;
+      else throw ConfigError{"gpu.schedule must be \"batched\" or \"sequential\""};
+    }
     if (g->find("windowRates")) s.windowRates = need(*g, "windowRates", slgpu_json::Value::Bool).b;
     if (g->find("csvThreads")) s.csvThreads = (uint32_t)need_uint(*g, "csvThreads");
     if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
@@ -504,6 +512,16 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
   return SLGPU_OK;
 }
 
+// sequential schedule: Sampler::step()'s model updates of the round just launched, in the reference's order
+slgpu_status sequential_scan(slgpu_engine* e) {
+  slgpu_tier::k_tier_scan_sequential<<<1, 32, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, e->cfg.nTemps, e->d_models, e->d_sig_w,
+                                                               e->d_ladder, e->P.sigma, e->P.beta, e->d_beta_values,
+                                                               e->cfg.optimalAcceptRate, e->cfg.optimalSwapRate);
+  CU_TRY(cudaGetLastError());
+  e->launches += 1;
+  return SLGPU_OK;
+}
+
 slgpu_status adapt_point(slgpu_engine* e) {
   const uint32_t T = e->cfg.nTemps;
   slgpu_tier::k_tier_adapt<<<dim3(T, 2, 9), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_sums, e->d_ticket, e->d_models,
@@ -670,6 +688,11 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     P.payload = e->d_payload;
     // sink
     e->seg_rounds = std::min(cfg.adaptInterval, cfg.maxRoundsPerLaunch);
+    if (cfg.sequential) {
+      e->seg_rounds = 1;  // the tier models are replayed chain by chain after every round
+      TRY_ST(dev_alloc(e, &e->d_beta_values, C));
+      e->state.push_back({"beta_values", e->d_beta_values, C * sizeof(double)});
+    }
     if (cfg.windowRates) {
       const size_t ringw = (size_t)slgpu_tier::kRingWords * C;
       TRY_ST(dev_alloc(e, &e->d_round_flags, (size_t)e->seg_rounds * C));
@@ -801,6 +824,8 @@ slgpu_status slgpu_init_chains(slgpu_engine* e) {
     return fail(SLGPU_E_CUDA, std::string("launch_init: ") + cudaGetErrorString((cudaError_t)rc));
   }
   e->launches++;
+  if (e->d_beta_values)  // computeBetaStack of the init loop (serverwrapper.cpp:71-72): values_ == the initial beta
+    CU_TRY(cudaMemcpyAsync(e->d_beta_values, e->P.beta, e->C * sizeof(double), cudaMemcpyDeviceToDevice, e->compute));
   if (emit) {
     e->rows_emitted += e->cfg.nStacks;
     if (to_host) {
@@ -834,7 +859,11 @@ slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds) {
     const uint64_t to_adapt = (A - (r + 2) % A) % A + 1;  // rounds up to and including the next adapt round
     const uint32_t n = (uint32_t)std::min<uint64_t>({left, to_adapt, (uint64_t)e->seg_rounds});
     if ((st = launch_rounds(e, n)) != SLGPU_OK) return st;
-    if ((e->rounds_done + 1) % A == 0 && (st = adapt_point(e)) != SLGPU_OK) return st;
+    if (e->cfg.sequential) {
+      if ((st = sequential_scan(e)) != SLGPU_OK) return st;
+    } else if ((e->rounds_done + 1) % A == 0 && (st = adapt_point(e)) != SLGPU_OK) {
+      return st;
+    }
     left -= n;
   }
   return SLGPU_OK;

@@ -195,6 +195,67 @@ __global__ void __launch_bounds__(256) k_tier_adapt(double* p_sig, double* p_bet
   if (tid == 0) compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
 }
 
+// ---- the reference's own schedule ("gpu": {"schedule": "sequential"}): a validation mode ----
+// RegressionAdapter::update for ONE sample, adaptive.cpp:63-78: x = (x0, x1, 1) with x0 = -clamp(logval), x1 = side.
+__device__ inline void model_update_one(double* m, double x0, double x1, double y) {
+  const double x[3] = {x0, x1, 1.0};
+  m[15] += 1.0;
+  const double alpha = 1.0 / m[15];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) m[3 * r + c] = m[3 * r + c] * (1.0 - alpha) + x[r] * x[c] * alpha;
+  for (int r = 0; r < 3; ++r) m[9 + r] = m[9 + r] * (1.0 - alpha) + x[r] * y * alpha;
+  qr_solve3(m, m + 9, m + 12);
+}
+
+// One thread replays what Sampler::step() does to the shared tier models after a round, chain by chain in the order
+// the reference's FIFO delivers results.  That order is data-independent: the constructor proposes chains C-1..0
+// (sampler.cpp:128-132), a chain re-enters the queue when it is processed (or, in a swap round, when its colder
+// neighbour unlocks it, sampler.cpp:237-257), so every round is processed in descending chain id.  The launch that
+// precedes this kernel advanced every chain by exactly ONE round, so p_sig / p_beta hold each chain's single
+// regression sample (x0 = P[2], x1 = P[4], y = P[8], P[5] = 1 if there was one).  Per chain, as sampler.cpp:158-186:
+//   sigmaAdapter.update, sigma[id] = computeSigma          (adaptive.cpp:63-78,134-139)
+//   if the chain was locked (swap round, t < T-1): betaAdapter.betaUpdate; at t == 0 computeBetaStack rewrites
+//   beta_values[stack][1..T-1]; then setBeta(id+1, beta_values[id+1]) -- so after a cascade beta[1] is new and
+//   beta[2..T-1] are the PREVIOUS ladder (values_ and ChainArray's beta differ; the reference's table prints values_).
+// Serial over S*T chains: for validation against the reference's schedule on small configurations only.
+__global__ void k_tier_scan_sequential(double* p_sig, double* p_beta, uint32_t S, uint32_t T, double* models, double* sig_w,
+                                       double* ladder, double* sigma, double* beta, double* beta_values, double opt_accept,
+                                       double opt_swap) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const uint32_t C = S * T;
+  for (uint32_t i = 0; i < C; ++i) {
+    const uint32_t id = C - 1 - i, s = id / T, t = id % T;
+    double* Ps = p_sig + (size_t)t * S + s;   // statistic k at Ps[k * T * S]
+    double* Pb = p_beta + (size_t)t * S + s;
+    const size_t ks = (size_t)T * S;
+    if (Ps[5 * ks] != 0.0) {
+      double* m = models + (size_t)t * kModelStride;
+      const double x1 = Ps[4 * ks];
+      model_update_one(m, Ps[2 * ks], x1, Ps[8 * ks]);
+      sigma[id] = slm_exp(model_predict(m + 12, opt_accept, kSigMinCap, kSigMaxCap, x1));
+      for (int k = 0; k < 9; ++k) Ps[k * ks] = 0.0;
+    }
+    if (Pb[5 * ks] != 0.0) {
+      double* m = models + (size_t)(T + t) * kModelStride;
+      model_update_one(m, Pb[2 * ks], Pb[4 * ks], Pb[8 * ks]);
+      if (t == 0) {
+        double logbeta = 0.0;
+        for (uint32_t j = 1; j < T; ++j) {
+          logbeta -= model_predict(models + (size_t)(T + j - 1) * kModelStride + 12, opt_swap, kBetaMinCap, kBetaMaxCap, logbeta);
+          beta_values[id + j] = slm_exp(logbeta);
+        }
+      }
+      beta[id + 1] = beta_values[id + 1];
+      for (int k = 0; k < 9; ++k) Pb[k * ks] = 0.0;
+    }
+  }
+  // what the batched kernels read as frozen weights: kept coherent with the models (their sigma / ladder results are
+  // overwritten by this kernel after every round)
+  for (uint32_t t = 0; t < T; ++t)
+    for (int j = 0; j < 3; ++j) sig_w[3 * t + j] = models[(size_t)t * kModelStride + 12 + j];
+  compute_ladder(models + (size_t)T * kModelStride, T, opt_swap, ladder);
+}
+
 // The acceptance windows of RegressionAdapter::update (adaptive.cpp:80-90), logging only: every chain keeps the last
 // accept flags of its sigma adapter (one per round) and of its beta adapter (one per swap attempt of the pair
 // (chain, chain+1)).  The reference's deque holds 999 flags once it has seen 1000 (it pushes, then pops when the size
