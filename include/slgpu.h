@@ -68,6 +68,9 @@ const char* slgpu_version(void);
  *   device (int, default 0)           seed (default 1234)        stackOffset (default 0)
  *   rng "philox" | "replay"           sink "device" | "host" | "csv" | "none" (default "device")
  *   adaptInterval (default swapInterval)   maxRoundsPerLaunch (default 64)
+ *   schedule "batched" (default: tier models frozen between adapt points) | "sequential" (validation mode: the
+ *     reference's own order, Sampler::step() src/infer/sampler.cpp:142-203 -- one round per launch, then the shared
+ *     tier models are replayed chain by chain; bit-identical to the reference's schedule, serial over the chains)
  *   hostRingRounds (default 8 * rounds per launch)   overwrite (bool, default false)
  * plugin_path: likelihood plugin .so; plugin_entry: its table symbol (NULL = "slgpu_plugin_entry").
  * payload: POD handed to the functor's constructor, copied to the device (may be NULL).
