@@ -89,6 +89,11 @@ def test_malformed_json_and_bad_values():
     assert _create(cfg)[0] == engine.E_CONFIG
     cfg = configs.engine_config(configs.workload("config1"), sink="tape")
     assert _create(cfg)[0] == engine.E_CONFIG
+    st, msg, _ = _create(configs.engine_config(configs.workload("config1"), schedule="eventually"))
+    assert st == engine.E_CONFIG and "schedule" in msg
+    # a valid schedule gets past the parser (and stops at the missing device on a CPU-only host)
+    st, msg, _ = _create(configs.engine_config(configs.workload("config1"), schedule="sequential"))
+    assert st != engine.E_CONFIG
 
 
 def test_plugin_errors():
