@@ -20,8 +20,6 @@ _LIB_PATH = os.path.join(_HERE, "_ref", "libsl_ref.so")
 REFERENCE_ROOT = os.environ.get("STATELINE_REFERENCE", "/root/reference")
 
 _dp = C.POINTER(C.c_double)
-_TARGET_FN = C.CFUNCTYPE(C.c_double, C.c_int32, _dp, C.c_uint32, C.c_uint32, C.c_uint32, _dp)
-_LIK_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_uint32, _dp, C.c_uint32)
 
 
 class SlrefConfig(C.Structure):
