@@ -82,6 +82,7 @@ def lib():
     L.slref_step_print.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.slref_get_logger.argtypes = [C.c_void_p] + [_dp] * 7
     L.slref_bouncy_bounds.argtypes = [_dp, _dp, _dp, C.c_uint32, _dp]
+    L.slref_epsr.argtypes = [_dp, C.c_uint32, C.c_uint32, C.c_uint32, _dp, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -206,3 +207,13 @@ def bouncy_bounds(val, mn, mx):
     out = np.empty_like(val)
     lib().slref_bouncy_bounds(_p(val), _p(mn), _p(mx), val.size, _p(out))
     return out
+
+
+def epsr(samples):
+    """EPSRDiagnostic of src/infer/diagnostics.cpp (object code): samples[n][m][d] -> (rhat[d], hasConverged)."""
+    x = _f64(samples)
+    n, m, d = x.shape
+    out = np.empty(d)
+    conv = C.c_int32(0)
+    lib().slref_epsr(_p(x), n, m, d, _p(out), C.byref(conv))
+    return out, bool(conv.value)

@@ -412,6 +412,22 @@ uint64_t slref_cold_rows(const slref_run* r, uint32_t stack, double* rows, uint6
 uint32_t slref_length(const slref_run* r, uint32_t chain) { return r->chains->length(chain); }
 
 /* stand-alone pieces */
+/* EPSRDiagnostic (src/infer/diagnostics.cpp) as the reference's own tests drive it (src/test/diagnostics.cpp):
+ * samples[n][m][d] fed round-robin to m cold chains (nChains = 1), rhat[d] out */
+void slref_epsr(const double* samples, uint32_t n, uint32_t m, uint32_t d, double* rhat, int32_t* converged) {
+  stateline::mcmc::EPSRDiagnostic epsr(m, 1, d);
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < m; ++j) {
+      stateline::mcmc::State state;
+      state.sample.resize(d);
+      for (uint32_t k = 0; k < d; ++k) state.sample[k] = samples[((size_t)i * m + j) * d + k];
+      epsr.update(j, state);
+    }
+  Eigen::ArrayXd rh = epsr.rHat();
+  for (uint32_t k = 0; k < d; ++k) rhat[k] = rh(k);
+  if (converged) *converged = epsr.hasConverged() ? 1 : 0;
+}
+
 void slref_bouncy_bounds(const double* val, const double* mn, const double* mx, uint32_t d, double* out) {
   Eigen::VectorXd v(d), a(d), b(d);
   for (uint32_t i = 0; i < d; ++i) { v[i] = val[i]; a[i] = mn[i]; b[i] = mx[i]; }
