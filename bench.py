@@ -170,6 +170,71 @@ def cpu_baseline_reference(budget_s):
     return steps / secs, cores, REF_SAMPLE % (cores, REF_STACKS_PER_PROC, 8, rounds, "")
 
 
+def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=60.0):
+    """The reference AS SHIPPED: stateline::ServerWrapper + (nproc - 1) stateline::WorkerWrapper over real ZeroMQ sockets
+    (oracle/_ref/ref_full: every reference source unmodified, oracle/Makefile.full), on `stacks` stacks x 8 temperatures
+    of config #3.  Returns (chain-steps/s, cores, sample) or None when the binary is absent.  The reference occasionally
+    stalls at start-up (a hello / heartbeat race): a run that exceeds timeout_s is killed and retried once."""
+    import socket
+    import subprocess
+    import tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(here, "oracle", "_ref", "ref_full")
+    if not os.path.exists(exe):
+        try:
+            from oracle import ref as R
+            if R.reference_present():
+                subprocess.check_call(["make", "-C", os.path.join(here, "oracle"), "-f", "Makefile.full", "-j8",
+                                       "REF=" + R.REFERENCE_ROOT], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+    if not os.path.exists(exe):
+        return None
+    import numpy as np
+    from stateline_b200 import configs
+    w = configs.workload(WORKLOAD, S=stacks)
+    cores = os.cpu_count() or 2
+    n_workers = max(1, cores - 1)
+    tmp = tempfile.mkdtemp(prefix="slfull_")
+    np.asarray(w["oracle_params"], dtype=np.float64).tofile(os.path.join(tmp, "params.bin"))
+
+    def run(rounds):
+        cfg = {"nStacks": w["S"], "nTemperatures": w["T"], "nSamplesTotal": w["S"] * rounds, "swapInterval": w["swapInterval"],
+               "loggingRateSec": 1e6, "nJobTypes": w["J"], "outputPath": tmp, "optimalAcceptRate": w["optAccept"],
+               "optimalSwapRate": w["optSwap"], "useInitial": False, "min": list(w["mn"]), "max": list(w["mx"])}
+        with open(os.path.join(tmp, "cfg.json"), "w") as f:
+            json.dump(cfg, f)
+        for _ in range(2):
+            with socket.socket() as sk:  # a free port for the delegator
+                sk.bind(("127.0.0.1", 0))
+                port = sk.getsockname()[1]
+            p = subprocess.Popen([exe, os.path.join(tmp, "cfg.json"), str(port), str(n_workers), str(int(w["oracle_target"])),
+                                  str(w["d"]), os.path.join(tmp, "params.bin")], stdout=subprocess.PIPE,
+                                 stderr=subprocess.DEVNULL, text=True, cwd=tmp)
+            try:
+                out, _ = p.communicate(timeout=timeout_s)
+                secs = float(out.split()[0])
+                return secs
+            except Exception:
+                p.kill()
+                p.wait()
+        raise RuntimeError("the reference's server + workers did not finish")
+
+    startup = 0.3 + 0.05 * n_workers  # the harness's own sleeps while it brings the workers up (oracle/ref_full.cpp)
+    t_small = run(20)
+    per_round = max((t_small - startup) / 20, 1e-4)
+    rounds = int(max(20, min(2000, budget_s / per_round)))
+    secs = run(rounds) - startup
+    steps = w["S"] * w["T"] * rounds
+    for f in os.listdir(tmp):
+        os.unlink(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return steps / secs, n_workers + 1, (
+        "%d stacks x %d temps of config #3, %d rounds (%d chain steps): the reference as shipped -- ServerWrapper + %d "
+        "WorkerWrapper over ZeroMQ (oracle/_ref/ref_full, all reference sources unmodified), chain initialisation included"
+        % (w["S"], w["T"], rounds, steps, n_workers))
+
+
 def ess_geyer(x):
     """Effective sample size of a 1-D series by Geyer's initial positive sequence."""
     import numpy as np
@@ -228,12 +293,19 @@ def run_reference_ref(args):
         pool.close()
     value = tot_steps / tot_s
     sample = REF_SAMPLE % (cores, REF_STACKS_PER_PROC, w["T"], rounds_per_step, " per step")
+    extra = {}
+    try:  # beside it: the reference as shipped (server + workers over ZeroMQ), a few seconds
+        full = cpu_baseline_full(budget_s=6.0)
+        if full:
+            extra["full_server_workers"] = {"value": full[0], "cores": full[1], "kind": "reference", "sample": full[2]}
+    except Exception as e:
+        sys.stderr.write("reference server + workers leg failed (%r)\n" % (e,))
     _emit(json.dumps({
         "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(w["T"], w["d"], w["J"], 8192),
-        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": dict({"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "reference", "sample": sample}, **extra),
         "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -493,6 +565,12 @@ def main():
         else:
             base["port_server_workers"] = port
         out["cpu_baseline"] = base
+        try:
+            full = cpu_baseline_full()
+            if full:
+                out["cpu_baseline"]["full_server_workers"] = {"value": full[0], "cores": full[1], "kind": "reference", "sample": full[2]}
+        except Exception as e:
+            sys.stderr.write("reference server + workers leg failed (%r)\n" % (e,))
         vi, si = cpu_baseline(0, 4.0)
         out["cpu_baseline"]["inline_1_thread"] = {"value": vi, "kind": "port", "sample": si}
     _emit(json.dumps(out))
