@@ -170,11 +170,12 @@ def cpu_baseline_reference(budget_s):
     return steps / secs, cores, REF_SAMPLE % (cores, REF_STACKS_PER_PROC, 8, rounds, "")
 
 
-def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=60.0):
+def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
     """The reference AS SHIPPED: stateline::ServerWrapper + (nproc - 1) stateline::WorkerWrapper over real ZeroMQ sockets
     (oracle/_ref/ref_full: every reference source unmodified, oracle/Makefile.full), on `stacks` stacks x 8 temperatures
     of config #3.  Returns (chain-steps/s, cores, sample) or None when the binary is absent.  The reference occasionally
-    stalls at start-up (a hello / heartbeat race): a run that exceeds timeout_s is killed and retried once."""
+    stalls at start-up (a hello / heartbeat race): a run that exceeds its time limit is killed and retried once; the leg
+    gives up (raises) after that, so it can add at most about a minute to a bench run."""
     import socket
     import subprocess
     import tempfile
@@ -198,7 +199,7 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=60.0):
     tmp = tempfile.mkdtemp(prefix="slfull_")
     np.asarray(w["oracle_params"], dtype=np.float64).tofile(os.path.join(tmp, "params.bin"))
 
-    def run(rounds):
+    def run(rounds, limit):
         cfg = {"nStacks": w["S"], "nTemperatures": w["T"], "nSamplesTotal": w["S"] * rounds, "swapInterval": w["swapInterval"],
                "loggingRateSec": 1e6, "nJobTypes": w["J"], "outputPath": tmp, "optimalAcceptRate": w["optAccept"],
                "optimalSwapRate": w["optSwap"], "useInitial": False, "min": list(w["mn"]), "max": list(w["mx"])}
@@ -212,7 +213,7 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=60.0):
                                   str(w["d"]), os.path.join(tmp, "params.bin")], stdout=subprocess.PIPE,
                                  stderr=subprocess.DEVNULL, text=True, cwd=tmp)
             try:
-                out, _ = p.communicate(timeout=timeout_s)
+                out, _ = p.communicate(timeout=limit)
                 secs = float(out.split()[0])
                 return secs
             except Exception:
@@ -221,10 +222,10 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=60.0):
         raise RuntimeError("the reference's server + workers did not finish")
 
     startup = 0.3 + 0.05 * n_workers  # the harness's own sleeps while it brings the workers up (oracle/ref_full.cpp)
-    t_small = run(20)
+    t_small = run(20, timeout_s)
     per_round = max((t_small - startup) / 20, 1e-4)
     rounds = int(max(20, min(2000, budget_s / per_round)))
-    secs = run(rounds) - startup
+    secs = run(rounds, max(timeout_s, 3.0 * budget_s)) - startup
     steps = w["S"] * w["T"] * rounds
     for f in os.listdir(tmp):
         os.unlink(os.path.join(tmp, f))
