@@ -142,8 +142,8 @@ void bouncy_bounds(const double* val, const double* mn, const double* mx, u32 d,
  * tools/fetch-deps:42-48) is not in the image; this restates the published algorithm: at step k the
  * remaining column of largest squared norm is swapped in, a Householder reflector zeroes the column
  * below the diagonal, norms are down-dated, pivots below eps*3*|max pivot| are treated as zero, then
- * Q^T b, back-substitution on the non-zero block and un-permutation.  Parity-unpinned (no reference
- * test covers it); any backward-stable solver agrees to cond*eps.
+ * Q^T b, back-substitution on the non-zero block and un-permutation.  Unpinned by Eigen itself (no reference
+ * test covers it; the Eigen stand-in of oracle/_ref uses this same restatement); any backward-stable solver agrees to cond*eps.
  * A is row-major.
  * ---------------------------------------------------------------------------------------------- */
 void qr_solve3(const double A[9], const double b[3], double w[3]) {

@@ -1,10 +1,10 @@
 """Generates the fixtures under tests/golden/ from the oracle (run from the repo root: python tests/golden/make_golden.py).
 
-The reference itself cannot be built in this image (Eigen and zmq.h are absent) and its own tests hold
-no sampler vectors, so these fixtures record the ORACLE's output with native Philox draws on small instances of
+These fixtures (oracle_*.json) record the ORACLE's output with native Philox draws on small instances of
 the five BASELINE workloads (the README demo config at its real size).  They pin the oracle against silent drift
 (any later change to oracle/ or to include/slgpu_math.h that alters a single bit fails
-tests/test_oracle.py::test_golden_fixture) and give the GPU tests a run-time-independent target."""
+tests/test_oracle.py::test_golden_fixture) and give the GPU tests a run-time-independent target.  The fixtures recorded
+from the REFERENCE'S OWN code (ref_*.json) are made by make_ref_golden.py."""
 import json
 import os
 import sys
