@@ -174,7 +174,7 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
     """The reference AS SHIPPED: stateline::ServerWrapper + (nproc - 1) stateline::WorkerWrapper over real ZeroMQ sockets
     (oracle/_ref/ref_full: every reference source unmodified, oracle/Makefile.full), on `stacks` stacks x 8 temperatures
     of config #3.  Returns (chain-steps/s, cores, sample) or None when the binary is absent.  The reference occasionally
-    stalls (about one run in ten here; the cause was not investigated): a run that exceeds its time limit is killed and retried once; the leg
+    stalls at start-up (the workers' hello is never registered: about one run in ten here; not investigated further): a run that exceeds its time limit is killed and retried once; the leg
     gives up (raises) after that, so it can add at most about a minute to a bench run."""
     import socket
     import subprocess
