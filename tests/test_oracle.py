@@ -247,3 +247,39 @@ def test_table_logger_format():
     assert body[8] == want
     assert lines[15] == "" and lines[16] == "Convergence test: %g (not converged)" % s.rhat().mean()
     assert lines[17:] == [""]
+
+
+def test_row_order_rank1_sweep_is_bit_identical():
+    """ProposalShaper::update (adaptive.cpp:184-197) sweeps columns; sweeping ROWS instead (row j: its off-diagonal
+    entries k = 0..j-1 left to right, then its own head) applies the same operations to every element in the same order.
+    The round-2 kernel plan (profiles/README.md) relies on this to walk the packed factor in memory order."""
+    import math
+    rng = np.random.default_rng(5)
+
+    def row_order(L, count, step):
+        d = L.shape[0]
+        L = L.copy()
+        count += 1.0
+        sq = math.sqrt(count)
+        x = [step[i] / sq for i in range(d)]
+        scale = math.sqrt((count - 1.0) / count)
+        c, s = [0.0] * d, [0.0] * d
+        for j in range(d):
+            xj = x[j]
+            for k in range(j):
+                Ljk = (L[j, k] * scale + s[k] * xj) / c[k]
+                L[j, k] = Ljk
+                xj = c[k] * xj - s[k] * Ljk
+            V = max(1e-18, L[j, j] * scale)
+            r = math.sqrt(V * V + xj * xj)
+            c[j], s[j] = r / V, xj / V
+            L[j, j] = r
+        return L
+
+    for d in (1, 2, 5, 20, 33, 50):
+        for t in range(8):
+            A = np.tril(rng.normal(size=(d, d))) * 0.3
+            A[np.diag_indices(d)] = np.abs(A.diagonal()) + 0.1
+            step = rng.normal(size=d) * rng.uniform(0.01, 3)
+            Lo, _, _ = O.shaper_update(A, 1000 + t, step, 2.5)
+            assert np.array_equal(np.tril(Lo), np.tril(row_order(A, 1000.0 + t, step)))
