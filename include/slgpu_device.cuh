@@ -212,16 +212,19 @@ struct HasWarpJobs : std::false_type {};
 template <class L>
 struct HasWarpJobs<L, std::void_t<decltype(&L::warp_jobs)>> : std::true_type {};
 
-/* base of chain c's packed L inside its 128-chain tile; consecutive entries are SLGPU_L_TILE doubles apart */
-__device__ __forceinline__ double* l_base(double* L, u32 c, u32 nL) {
-  return L + (size_t)(c / SLGPU_L_TILE) * nL * SLGPU_L_TILE + (c % SLGPU_L_TILE);
+/* base of chain (stack s, temperature t)'s packed L inside its stack group's tile (slgpu_plugin.h); consecutive
+ * entries are SLGPU_L_TILE doubles apart */
+__device__ __forceinline__ double* l_base(double* L, u32 n_temps, u32 s, u32 t, u32 nL) {
+  const u32 spw = 32u / n_temps;
+  return L + (size_t)(s / spw) * nL * SLGPU_L_TILE + (s % spw) * n_temps + t;
 }
 
-/* entry (r,k), k <= r, of chain c's factor in whichever layout the dimension uses */
-__device__ __forceinline__ double& l_elem(double* L, u32 c, int d, int r, int k) {
+/* entry (r,k), k <= r, of chain (s,t)'s factor in whichever layout the dimension uses */
+__device__ __forceinline__ double& l_elem(double* L, u32 n_temps, u32 s, u32 t, int d, int r, int k) {
   const size_t nL = (size_t)d * (d + 1) / 2;
-  if (SLGPU_L_LAYOUT((u32)d) == SLGPU_L_COLMAJOR) return L[(size_t)c * nL + (size_t)k * d - (size_t)k * (k - 1) / 2 + (size_t)(r - k)];
-  return l_base(L, c, (u32)nL)[(size_t)(r * (r + 1) / 2 + k) * SLGPU_L_TILE];
+  if (SLGPU_L_LAYOUT((u32)d) == SLGPU_L_COLMAJOR)
+    return L[(size_t)(s * n_temps + t) * nL + (size_t)k * d - (size_t)k * (k - 1) / 2 + (size_t)(r - k)];
+  return l_base(L, n_temps, s, t, (u32)nL)[(size_t)(r * (r + 1) / 2 + k) * SLGPU_L_TILE];
 }
 
 /* regression statistics: P[(k*T + t)*S + s], k < 9 -- coalesced over the stacks of a tier for the reduce */
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
     p.x[(size_t)i * C + c] = x[i];
   for (int r = 0; r < d; ++r)
     for (int k = 0; k <= r; ++k)
-      l_elem(p.L, c, d, r, k) = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
+      l_elem(p.L, p.n_temps, m.s, (u32)m.t, d, r, k) = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
   const double b = p.ladder[m.t];
   p.energy[c] = e;
   p.row_sigma[c] = 1.0;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
   __syncthreads();
 
   const Lik lik(p.payload);
-  double* __restrict__ Lc = l_base(p.L, c, (u32)(d * (d + 1) / 2));
+  double* __restrict__ Lc = l_base(p.L, p.n_temps, m.active ? m.s : 0u, (u32)m.t, (u32)(d * (d + 1) / 2)); /* idle lanes shadow chain 0 */
   const size_t ls = SLGPU_L_TILE;
 
   double x[DM];
@@ -562,9 +565,14 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_step_kernel(const slgpu_step
 
 }  // namespace slgpu
 
+/* d <= 32, compile-time dimension: the thread-per-chain kernel (slgpu_step_fast.cuh) is the default; building a plugin
+ * with -DSLGPU_TILE_KERNEL selects the block-per-stack-group kernel with the factors resident in shared memory
+ * (slgpu_step_tile.cuh): same bits, HBM traffic = algorithmic, 1.9x the time on config #3 (profiles/README.md) */
+#ifdef SLGPU_TILE_KERNEL
+#include "slgpu_step_tile.cuh"
+#else
 #include "slgpu_step_fast.cuh"
-#include "slgpu_step_pair.cuh"
-#include "slgpu_step_quad.cuh"
+#endif
 #include "slgpu_step_warp.cuh"
 
 namespace slgpu {
@@ -586,26 +594,6 @@ inline unsigned grid_for(const slgpu_step_params* p, unsigned threads = SLGPU_TH
   return (p->n_stacks + per_block - 1) / per_block;
 }
 
-#ifndef SLGPU_DEFAULT_PAIR
-#define SLGPU_DEFAULT_PAIR 0
-#endif
-#ifndef SLGPU_DEFAULT_QUAD
-#define SLGPU_DEFAULT_QUAD 0
-#endif
-
-/* development switch: SLGPU_STEP_VARIANT = generic | single | pair picks the step kernel */
-inline int step_variant() {
-  const char* v = getenv("SLGPU_STEP_VARIANT");
-  if (!v) return 0;
-  if (!strcmp(v, "smem")) return 1;
-  if (!strcmp(v, "global")) return 2;
-  if (!strcmp(v, "generic")) return 3;
-  if (!strcmp(v, "pair")) return 4;
-  if (!strcmp(v, "single")) return 5;
-  if (!strcmp(v, "quad")) return 6;
-  return 0;
-}
-
 /* host launchers instantiated per (functor, compile-time dimension); D = 0 is the runtime-d kernel */
 template <class Lik, int D>
 int launch_init_t(const slgpu_step_params* p, void* stream) {
@@ -622,11 +610,9 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
 #define SLGPU_WARP_LAUNCH(RMV, MAXTV)                                                                                     \
   {                                                                                                                       \
     auto kern = pt_step_warp_kernel<Lik, RMV, MAXTV>;                                                                     \
-    static size_t attr_set = 48 * 1024;                                                                                   \
-    if (smem > attr_set) {                                                                                                \
+    if (smem > 48 * 1024) { /* per device and context: set on every launch (a process may drive several devices) */      \
       const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
       if (attr != cudaSuccess) return (int)attr;                                                                          \
-      attr_set = smem;                                                                                                    \
     }                                                                                                                     \
     kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*p);                                                              \
   }
@@ -640,48 +626,22 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
 #undef SLGPU_WARP_LAUNCH
     return (int)cudaGetLastError();
   }
-  constexpr int JS = StaticJobs<Lik, D>::value;
-  if (JS > 0 && p->n_job_types != (uint32_t)JS) {
-    pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
-    return (int)cudaGetLastError();
-  }
   if constexpr (D > 0 && D <= 32) {
-    const int variant = step_variant();
-    if ((variant == 6 || (variant == 0 && SLGPU_DEFAULT_QUAD)) && p->n_temps <= 8) { /* L in shared memory, four lanes per chain */
-      constexpr int NT = SLGPU_QUAD_THREADS;
-      auto kern = pt_step_quad_kernel<Lik, D, NT>;
-      const size_t smem = quad_smem_bytes<D, NT>(p->n_temps, p->n_job_types);
-      if (smem <= 200 * 1024) {
-        static size_t attr_set = 0;
-        if (smem > attr_set) {
-          const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (attr != cudaSuccess) return (int)attr;
-          attr_set = smem;
-        }
-        const unsigned spw = 8u / p->n_temps, per_block = spw * (NT / 32);
-        kern<<<(p->n_stacks + per_block - 1) / per_block, NT, smem, (cudaStream_t)stream>>>(*p);
-        return (int)cudaGetLastError();
-      }
-    }
-    if ((variant == 4 || (variant == 0 && SLGPU_DEFAULT_PAIR)) && p->n_temps <= 16) { /* two lanes per chain */
-      constexpr int NT = SLGPU_PAIR_THREADS;
-      auto kern = pt_step_pair_kernel<Lik, D, NT>;
-      const size_t smem = pair_smem_bytes<D, NT>(p->n_temps);
-      static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes<D, NT>(1));
-      if (attr != cudaSuccess) return (int)attr;
-      const unsigned spw = 16u / p->n_temps, per_block = spw * (NT / 32);
-      kern<<<(p->n_stacks + per_block - 1) / per_block, NT, smem, (cudaStream_t)stream>>>(*p);
-      return (int)cudaGetLastError();
-    }
-    if (variant != 3) {
+#ifdef SLGPU_TILE_KERNEL
+    return launch_step_tile<Lik, D>(p, stream);
+#else
+    constexpr int JS = StaticJobs<Lik, D>::value;
+    if (!(JS > 0 && p->n_job_types != (uint32_t)JS)) {
       constexpr int NT = SLGPU_FAST_THREADS;
       auto kern = pt_step_fast_kernel<Lik, D, NT>;
       const size_t smem = fast_smem_bytes<D, NT>(p->n_temps);
-      static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<D, NT>(1));
+      /* the opt-in is per device and context: set it on every launch (a process may drive several devices) */
+      const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<D, NT>(1));
       if (attr != cudaSuccess) return (int)attr;
       kern<<<grid_for(p, NT), NT, smem, (cudaStream_t)stream>>>(*p);
       return (int)cudaGetLastError();
     }
+#endif
   }
   pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
   return (int)cudaGetLastError();

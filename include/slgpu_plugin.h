@@ -22,15 +22,21 @@
 extern "C" {
 #endif
 
-#define SLGPU_PLUGIN_ABI 3u
+#define SLGPU_PLUGIN_ABI 4u
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
-#define SLGPU_L_TILE 128u   /* chains per tile of the packed-L store (see slgpu_step_params.L) */
-/* how the packed L factors are stored (slgpu_step_params.L): small dimensions are tiled by 128 chains for the
- * thread-per-chain kernels; large ones are kept per chain, packed column-major, for the warp-per-chain kernel */
+#define SLGPU_L_TILE 32u    /* chain slots per tile of the packed-L store (see slgpu_step_params.L) */
+/* how the packed L factors are stored (slgpu_step_params.L): small dimensions are tiled by stack group (the
+ * floor(32 / n_temps) stacks whose chains share a warp) for the tile kernel, which keeps a group's tile in shared
+ * memory for a whole launch; large ones are kept per chain, packed column-major, for the warp-per-chain kernel */
 #define SLGPU_L_TILED 0
 #define SLGPU_L_COLMAJOR 1
 #define SLGPU_L_LAYOUT(n_dims) ((n_dims) > 32u ? SLGPU_L_COLMAJOR : SLGPU_L_TILED)
+/* doubles in the L store of n_stacks x n_temps chains of dimension n_dims */
+#define SLGPU_L_DOUBLES(n_stacks, n_temps, n_dims)                                                                      \
+  (SLGPU_L_LAYOUT(n_dims) == SLGPU_L_COLMAJOR                                                                           \
+       ? (((size_t)(n_stacks) * (n_temps) + 127u) / 128u * 128u) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u)           \
+       : (size_t)(((n_stacks) + 32u / (n_temps) - 1u) / (32u / (n_temps))) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u) * SLGPU_L_TILE)
 #define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
 
 enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
@@ -39,9 +45,11 @@ enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
  * Chain id = stack * n_temps + temperature, temperature 0 coldest (src/infer/chainarray.hpp:28-37).
  * C = n_stacks * n_temps.  Per-chain arrays are indexed [chain]; vectors and matrices are stored
  * structure-of-arrays, element-major: x[i * C + chain]; the packed lower triangle of L (row-major, nL =
- * d(d+1)/2 entries) is tiled by 128 chains, L[((chain / 128) * nL + r*(r+1)/2 + k) * 128 + chain % 128], so a
- * warp reads one 256-byte line per entry, a thread block's factors are one contiguous region and
- * the entry offsets inside a tile are compile-time constants; p_sig[(k * T + temp) * S + stack], ep_m[i * n_stacks + stack]. */
+ * d(d+1)/2 entries) is tiled by stack group: with spw = 32 / n_temps stacks per group, chain (stack, temp) is slot
+ * (stack % spw) * n_temps + temp of tile stack / spw, and entry (r,k) of its factor is
+ * L[((stack / spw) * nL + r*(r+1)/2 + k) * 32 + slot] -- a group's factors are one contiguous tile of nL * 256 bytes
+ * (one bulk copy into shared memory) and a warp reads one 256-byte line per entry;
+ * p_sig[(k * T + temp) * S + stack], ep_m[i * n_stacks + stack]. */
 typedef struct slgpu_step_params {
   uint32_t n_stacks, n_temps, n_dims, n_job_types;
   uint32_t swap_interval;  /* swap sweep in the round that makes the chain length a multiple of it */
@@ -61,7 +69,7 @@ typedef struct slgpu_step_params {
   /* chain state */
   double* x;               /* [d][C]  sample of the last row */
   double* L;               /* ProposalShaper L_ (adaptive.cpp:158), lower triangle.  d <= 32 (SLGPU_L_TILED):
-                            * [ceil(C/128)][d(d+1)/2][128], row-major packed.  d > 32 (SLGPU_L_COLMAJOR):
+                            * [ceil(S/spw)][d(d+1)/2][32], row-major packed.  d > 32 (SLGPU_L_COLMAJOR):
                             * [C][d(d+1)/2], column-major packed: L(j,k) at k*d - k(k-1)/2 + (j-k) */
   double* energy;          /* [C] */
   double* row_sigma;       /* [C] sigma stored in the last row (stale after a reject, chainarray.cpp:102-106) */

@@ -257,11 +257,9 @@ __device__ __forceinline__ double shaper_update_pair2(double* Lc, double* xs, in
   return prop_norm / smax(frob, eps);
 }
 
-/* chain of thread slot ct of this block under ThreadMap (only called for active slots) */
-__device__ __forceinline__ u32 thread_chain(const slgpu_step_params& p, u32 blk, int ct) {
-  const int T = (int)p.n_temps, spw = 32 / T, lane = ct & 31, sl = lane / T, t = lane - sl * T;
-  const u32 s = (blk * (blockDim.x >> 5) + (u32)(ct >> 5)) * (u32)spw + (u32)sl;
-  return s * (u32)T + (u32)t;
+/* factor of the chain of thread slot ct of this block under ThreadMap (only called for active slots) */
+__device__ __forceinline__ double* thread_l_base(const slgpu_step_params& p, u32 blk, int ct, u32 nL) {
+  return p.L + (size_t)(blk * (blockDim.x >> 5) + (u32)(ct >> 5)) * nL * SLGPU_L_TILE + (ct & 31);
 }
 
 #ifdef SLGPU_STAMPS /* development: block-level time stamps (ns) into the round_flags buffer, 32 u64 per block */
@@ -329,7 +327,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   __syncthreads();
 
   const Lik lik(p.payload);
-  const double* Lc = l_base(p.L, c, D * (D + 1) / 2); /* rewritten by other threads in phase B: no __restrict__ */
+  const double* Lc = l_base(p.L, p.n_temps, active ? m.s : 0u, (u32)m.t, D * (D + 1) / 2); /* rewritten by other threads in phase B: no __restrict__ */
 #pragma unroll
   for (int i = 0; i < D; ++i) s_x[i * NX + tid] = p.x[(size_t)i * C + c];
   if (active && m.t == 0) {
@@ -449,7 +447,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #ifndef SLGPU_PHASEB_PAIR /* measured on config #3: one lane per staged chain 59.7 us per round, a lane pair 68.8 */
       if (mine) { /* jump in s_jump[.][slot] */
         const int own = s_owner[slot];
-        s_nsc[own] = shaper_update_rolled<D>(l_base(p.L, thread_chain(p, blk, own), D * (D + 1) / 2), s_jump + slot, NT, s_cnt[slot], p.prop_norm);
+        s_nsc[own] = shaper_update_rolled<D>(thread_l_base(p, blk, own, D * (D + 1) / 2), s_jump + slot, NT, s_cnt[slot], p.prop_norm);
       }
 #else
       (void)mine;
@@ -457,7 +455,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
        * in column u of s_z (every z is dead by now) */
       const unsigned pm = 3u << (m.lane & ~1);
       for (int u = tid >> 1; u < nacc; u += NT / 2) {
-        const double ns = shaper_update_pair2<D>(l_base(p.L, thread_chain(p, blk, s_owner[u]), D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
+        const double ns = shaper_update_pair2<D>(thread_l_base(p, blk, s_owner[u], D * (D + 1) / 2), s_jump + u, NT, s_z + u, NT, s_cnt[u],
                                                  p.prop_norm, tid & 1, pm);
         if ((tid & 1) == 0) s_nsc[s_owner[u]] = ns;
       }

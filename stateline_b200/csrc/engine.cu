@@ -651,9 +651,10 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     TRY_ST(dev_alloc(e, &d_n0, d)); TRY_ST(upload(d_n0, n0));
     if (cfg.useInitial) { TRY_ST(dev_alloc(e, &d_init, d)); TRY_ST(upload(d_init, cfg.initial)); }
     P.mn = d_mn; P.mx = d_mx; P.n0_diag = d_n0; P.initial = d_init;
-    const size_t nL = (size_t)d * (d + 1) / 2;
     TRY_ST(dev_alloc(e, &P.x, d * C));
-    TRY_ST(dev_alloc(e, &P.L, nL * ((C + SLGPU_L_TILE - 1) / SLGPU_L_TILE) * SLGPU_L_TILE));
+    const size_t nLall = SLGPU_L_DOUBLES(S, T, d);
+    TRY_ST(dev_alloc(e, &P.L, nLall));
+    CU_TRY(cudaMemset(P.L, 0, nLall * sizeof(double)));  // the idle slots of a tile travel with it: keep them defined
     TRY_ST(dev_alloc(e, &P.energy, C)); TRY_ST(dev_alloc(e, &P.row_sigma, C)); TRY_ST(dev_alloc(e, &P.row_beta, C));
     TRY_ST(dev_alloc(e, &P.sigma, C)); TRY_ST(dev_alloc(e, &P.beta, C)); TRY_ST(dev_alloc(e, &P.nscale, C));
     TRY_ST(dev_alloc(e, &P.sh_count, C));
@@ -671,7 +672,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     P.sig_w = e->d_sig_w;
     P.ladder = e->d_ladder;
     {
-      const size_t nLall = nL * ((C + SLGPU_L_TILE - 1) / SLGPU_L_TILE) * SLGPU_L_TILE, f8 = sizeof(double), i4 = sizeof(int32_t);
+      const size_t f8 = sizeof(double), i4 = sizeof(int32_t);
       e->state = {{"x", P.x, d * C * f8}, {"L", P.L, nLall * f8}, {"energy", P.energy, C * f8}, {"row_sigma", P.row_sigma, C * f8},
                   {"row_beta", P.row_beta, C * f8}, {"sigma", P.sigma, C * f8}, {"beta", P.beta, C * f8}, {"nscale", P.nscale, C * f8},
                   {"sh_count", P.sh_count, C * f8}, {"accepted", P.accepted, C * i4}, {"swap_type", P.swap_type, C * i4},
@@ -1028,7 +1029,8 @@ slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double
     for (size_t k = 0; k < d; ++k)
       for (size_t j = k; j < d; ++j) packed[j * (j + 1) / 2 + k] = colp[k * d - k * (k - 1) / 2 + (j - k)];
   } else {
-    const double* lsrc = e->P.L + (size_t)(chain / SLGPU_L_TILE) * nL * SLGPU_L_TILE + chain % SLGPU_L_TILE;
+    const uint32_t T = e->cfg.nTemps, spw = 32u / T, stack = chain / T;  // tile = stack group, slot = lane of the chain
+    const double* lsrc = e->P.L + (size_t)(stack / spw) * nL * SLGPU_L_TILE + (stack % spw) * T + chain % T;
     CU_TRY(cudaMemcpy2D(packed.data(), sizeof(double), lsrc, SLGPU_L_TILE * sizeof(double), sizeof(double), nL, cudaMemcpyDeviceToHost));
   }
   double cnt = 0.0, ns = 0.0;
@@ -1337,7 +1339,7 @@ CkHeader ck_header(const slgpu_engine* e) {
   std::memset(&h, 0, sizeof h);
   std::memcpy(h.magic, kCkMagic, 8);
   const Settings& c = e->cfg;
-  h.version = 1;
+  h.version = 2;  // 2: L tiled by stack group (SLGPU_L_TILE 32)
   h.n_stacks = c.nStacks; h.n_temps = c.nTemps; h.n_dims = c.nDims; h.n_job_types = c.nJobTypes;
   h.swap_interval = c.swapInterval; h.adapt_interval = c.adaptInterval; h.stack_offset = c.stackOffset;
   h.l_layout = SLGPU_L_LAYOUT(c.nDims); h.rng = (uint32_t)c.rng;
@@ -1399,7 +1401,7 @@ slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
   FileCloser fc{std::fopen(path, "rb")};
   if (!fc.f) return fail(SLGPU_E_IO, std::string("cannot open ") + path);
   CkHeader h;
-  if (std::fread(&h, sizeof h, 1, fc.f) != 1 || std::memcmp(h.magic, kCkMagic, 8) != 0 || h.version != 1)
+  if (std::fread(&h, sizeof h, 1, fc.f) != 1 || std::memcmp(h.magic, kCkMagic, 8) != 0 || h.version != 2)
     return fail(SLGPU_E_IO, std::string(path) + " is not a slgpu checkpoint");
   CkHeader want = ck_header(e);
   want.rounds_done = h.rounds_done;

@@ -91,22 +91,6 @@ def test_philox_bit_exact(name, rounds):
         _compare(eng, orc, w, "philox %d rounds" % rounds)
 
 
-def test_step_kernel_variants_agree(monkeypatch):
-    """The runtime-d kernel, the thread-per-chain kernel, the lane-pair kernel and the shared-memory
-    lane-quad kernel are the same function: bit-identical state, rows and factors."""
-    w = configs.workload("config3", S=12)
-    res = []
-    for variant in ("generic", "single", "pair", "quad"):
-        monkeypatch.setenv("SLGPU_STEP_VARIANT", variant)
-        with engine_for(w, seed=3) as eng:
-            eng.init_chains()
-            eng.step_rounds(59)
-            res.append((eng.last_rows(), eng.drain(), eng.shaper(5)[0]))
-    for other in res[1:]:
-        for a, b in zip(res[0], other):
-            assert np.array_equal(a, b)
-
-
 GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(HERE, "golden")) if f.startswith("oracle_") and f.endswith(".json"))
 
 
@@ -258,3 +242,49 @@ def test_zero_rounds_and_empty_run():
         eng.step_rounds(0)
         assert eng.rounds_done == 0
         assert eng.drain().shape == (w["S"], w["d"] + 5)  # only the initial rows
+
+
+def _compare_all_rows(eng, orc, w, rounds):
+    rows = eng.drain().reshape(rounds + 1, w["S"], w["d"] + 5)
+    for s in range(w["S"]):
+        assert np.array_equal(rows[:, s], orc.cold_rows(s)), "cold rows of stack %d" % s
+
+
+# BASELINE.json's sizes, bit for bit against the oracle: the bench configuration itself (#3 at 8192 x 8 crosses two
+# adapt points in 21 rounds and three in 31), #4 at 1024 x 8 and #5 at 8192 x 16 (one GPU's share).  At these sizes
+# k_tier_adapt's reduce slots hold 32 / 4 / 32 stacks each, the grids are several waves deep and every block stages a
+# realistic number of accepted chains -- none of which the small shapes above reach.
+@pytest.mark.parametrize("name,S,rounds", [("config3", 8192, 21), ("config3", 8192, 31), ("config4", 1024, 11), ("config5", 8192, 4)])
+def test_baseline_sizes_bit_exact(name, S, rounds):
+    w = configs.workload(name, S=S)
+    orc = oracle_for(w, seed=1234)
+    orc.init_chains()
+    orc.run_rounds(rounds)
+    with engine_for(w, seed=1234, hostRingRounds=rounds + 2) as eng:
+        eng.init_chains()
+        eng.step_rounds(rounds)
+        _compare(eng, orc, w, "%s at S=%d after %d rounds" % (name, S, rounds))
+        _compare_all_rows(eng, orc, w, rounds)
+        # every chain's factor, not only three of them: the scale the next proposal uses is a function of all of L
+        rng = np.random.default_rng(S + rounds)
+        for chain in rng.integers(0, w["S"] * w["T"], 24):
+            gL, gN, gcnt = eng.shaper(int(chain))
+            oL, oN, ocnt = orc.shaper(int(chain))
+            assert gcnt == ocnt and np.array_equal(gL, oL) and np.array_equal(gN, oN), chain
+
+
+@pytest.mark.parametrize("S", [257, 1000, 4099])
+def test_tier_reduce_across_many_stacks(S):
+    """k_tier_adapt's cross-stack sum against the oracle's reduce_tree256 when a slot holds several stacks and S is
+    not a multiple of 256: the tier models (mu_xx, mu_xy, weights, counts) after three adapt points, bit for bit."""
+    d, T, J = 3, 4, 2
+    w = dict(S=S, T=T, d=d, J=J, mn=[-2.0, -1.5, -3.0], mx=[2.5, 1.0, 3.0], swapInterval=5, optAccept=0.25, optSwap=0.4,
+             plugin="demo_gauss", payload=None, oracle_target=configs.T_DEMO_GAUSS, oracle_params=None)
+    orc = oracle_for(w, seed=S)
+    orc.init_chains()
+    orc.run_rounds(16)
+    with engine_for(w, seed=S, hostRingRounds=20) as eng:
+        eng.init_chains()
+        eng.step_rounds(16)
+        _compare(eng, orc, w, "tier reduce S=%d" % S)
+        _compare_all_rows(eng, orc, w, 16)
