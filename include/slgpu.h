@@ -72,6 +72,13 @@ const char* slgpu_version(void);
  *     reference's own order, Sampler::step() src/infer/sampler.cpp:142-203 -- one round per launch, then the shared
  *     tier models are replayed chain by chain; bit-identical to the reference's schedule, serial over the chains)
  *   hostRingRounds (default 8 * rounds per launch)   overwrite (bool, default false)
+ *   wire "delta" (default) | "full": what the copy engine carries to the host for sink host / csv / bin.  "full" = every
+ *     cold row, d + 5 doubles.  "delta" = one flag byte per row plus the d + 3 doubles of a row only when the cold
+ *     state changed (a rejected proposal re-pushes a copy of the last state, src/infer/chainarray.cpp:102-106, so about
+ *     three rows in four repeat); slgpu_drain / slgpu_peek / the csv files rebuild the exact rows on the host and are
+ *     byte-identical for both settings.  With overwrite every segment starts with a full set of rows.
+ *   sink "bin": the delta stream appended to <outputPath>/chains-<stackOffset>.slgpu as it lands (stateline_b200/binlog.py
+ *     reads it back into rows); the sink that keeps up with the GPU, csv is for small runs
  * plugin_path: likelihood plugin .so; plugin_entry: its table symbol (NULL = "slgpu_plugin_entry").
  * payload: POD handed to the functor's constructor, copied to the device (may be NULL).
  */
@@ -101,6 +108,29 @@ slgpu_status slgpu_drain(slgpu_engine* e, double* rows, size_t cap_rows, size_t*
 slgpu_status slgpu_peek(slgpu_engine* e, const double** span0, size_t* n0, const double** span1, size_t* n1);
 slgpu_status slgpu_advance(slgpu_engine* e, size_t n_rows);
 uint64_t slgpu_rows_emitted(const slgpu_engine* e); /* rows produced on the device so far */
+
+/* ---- the delta stream itself (sink "host", wire "delta"): zero-copy view of the oldest landed segment in the pinned
+ * ring, for consumers that do not want the rows rebuilt.  A segment covers the cold rows of one launch, rows
+ * row_begin .. row_begin + n_rounds * n_stacks - 1 in emission order:
+ *   flags[round * n_stacks + stack]   bit 0 accepted, bits 1-2 swapType, bit 3 "changed"
+ *   payload[slot * payload_doubles]   x_0..x_{d-1}, energy, sigma, beta of a changed row
+ *   base[round * n_chunks + chunk]    slot of the first changed row among stacks 256 * chunk .. 256 * chunk + 255 of that
+ *                                     round; the next changed row of the chunk has the next slot
+ * An unchanged row repeats x, energy, sigma, beta of the same stack's previous row (src/infer/chainarray.cpp:102-106);
+ * a key segment (key != 0: the first one, the first after slgpu_load_state, every one with gpu.overwrite) marks all rows
+ * of its first round changed.  slgpu_next_segment leaves n_rounds = 0 when nothing has landed (block = 0) or nothing is
+ * queued; slgpu_release_segment frees the ring space.  Mixing with slgpu_drain is allowed at segment boundaries. */
+typedef struct slgpu_segment {
+  uint32_t n_rounds, n_stacks, n_chunks, payload_doubles, count, key;
+  uint64_t row_begin;
+  const uint32_t* base;
+  const unsigned char* flags;
+  const double* payload;
+} slgpu_segment;
+slgpu_status slgpu_next_segment(slgpu_engine* e, int block, slgpu_segment* out);
+slgpu_status slgpu_release_segment(slgpu_engine* e);
+/* bytes handed to the copy engine for the row sink so far (what `e2e.d2h_bytes_per_step` of bench.py counts) */
+uint64_t slgpu_d2h_bytes(const slgpu_engine* e);
 
 /* ---- device-side timing of what was queued between the two calls (CUDA events on the compute stream) ---- */
 slgpu_status slgpu_timer_start(slgpu_engine* e);

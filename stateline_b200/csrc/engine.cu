@@ -35,6 +35,7 @@
 #include "json_min.hpp"
 #include "slgpu.h"
 #include "slgpu_plugin.h"
+#include "row_compact.cuh"
 #include "tier_kernels.cuh"
 
 namespace {
@@ -54,7 +55,11 @@ slgpu_status fail(slgpu_status st, const std::string& msg) {
   } while (0)
 
 constexpr int kSegments = 3;
-enum Sink { SINK_NONE, SINK_DEVICE, SINK_HOST, SINK_CSV };
+constexpr int kCompactBufs = kSegments + 1;  // see enqueue_compact: a buffer is reused only after the host has seen its segment land
+enum Sink { SINK_NONE, SINK_DEVICE, SINK_HOST, SINK_CSV, SINK_BIN };
+// what crosses PCIe for a host-side sink: every cold row in full, or (default) the delta stream -- one flag byte per row
+// and the d + 3 doubles of a row only when the cold state changed (k_compact_rows)
+enum Wire { WIRE_DELTA, WIRE_FULL };
 
 struct Settings {
   // src/app/serverwrapper.hpp:64-91
@@ -70,6 +75,7 @@ struct Settings {
   uint32_t stackOffset = 0;
   int rng = SLGPU_RNG_PHILOX;
   Sink sink = SINK_DEVICE;
+  Wire wire = WIRE_DELTA;
   uint32_t adaptInterval = 0, maxRoundsPerLaunch = 64;
   uint64_t hostRingRounds = 0;
   bool overwrite = false;
@@ -88,6 +94,43 @@ struct Segment {
 struct PendingCopy {
   cudaEvent_t ev;
   uint64_t rows_end;
+};
+
+// ---- the delta stream (wire "delta") -------------------------------------------------------------------------------
+// On a reject ChainArray::append re-pushes a copy of the last state (src/infer/chainarray.cpp:102-106): about three
+// cold rows in four repeat the row before them in everything but the two flags.  After every launch k_compact_rows
+// turns the launch's full rows (device segment) into a compact segment, which is what the copy engine moves:
+//   header  { u32 n_rounds, n_stacks, count, key }            count = payload rows
+//   base    u32 [n_rounds][n_chunks]                          payload slot of the first changed row of a chunk of 256 stacks
+//   flags   u8  [n_rounds][n_stacks]                          bit 0 accepted, bits 1-2 swapType, bit 3 changed
+//   payload f64 [count][d + 3]                                x, energy, sigma, beta of the changed rows, in (round, chunk, stack) order within a chunk
+// "changed" = any of the d + 3 doubles differs bitwise from the same stack's previous row (the previous launch's last
+// round for round 0; a key segment marks every row of its first round changed).  The host rebuilds the exact d + 5
+// doubles of every row (materialise), or hands the segment out as it is (slgpu_next_segment).
+struct SegLayout {
+  uint32_t n_chunks = 0;
+  size_t off_base = 16, off_flags = 0, off_payload = 0;
+  size_t bytes(uint32_t payload_rows, uint32_t d) const { return off_payload + (size_t)payload_rows * (d + 3) * sizeof(double); }
+};
+inline SegLayout seg_layout(uint32_t n_rounds, uint32_t S) {
+  SegLayout L;
+  L.n_chunks = (S + 255u) / 256u;
+  L.off_flags = (16 + (size_t)n_rounds * L.n_chunks * 4 + 15) / 16 * 16;
+  L.off_payload = (L.off_flags + (size_t)n_rounds * S + 15) / 16 * 16;
+  return L;
+}
+struct CompactBuf {
+  unsigned char* dev = nullptr;
+  cudaEvent_t written = nullptr, copied = nullptr;
+  bool copy_pending = false;
+};
+struct HostSeg {  // one compact segment in the pinned byte ring, oldest first
+  size_t off = 0, reserved = 0;   // region of the byte ring
+  uint32_t n_rounds = 0, cap_copied = 0;  // payload rows covered by the first copy
+  uint64_t row_begin = 0;         // global index of its first row
+  const unsigned char* dev = nullptr;  // where the rest of the payload would come from
+  cudaEvent_t ev = nullptr;       // the copy (or the remainder copy) has landed
+  bool landed = false, remainder = false;
 };
 
 // one device array of the sampler state, as written to / read from a checkpoint
@@ -139,12 +182,25 @@ struct slgpu_engine {
   size_t C = 0;
   Segment seg[kSegments];
   uint64_t seg_next = 0;
-  // host ring (sink host / csv)
+  // host ring (sink host / csv): full rows.  Wire "full": pinned, the copy engine writes it.  Wire "delta": pageable,
+  // allocated on first use and filled by materialise() from the compact segments of the pinned byte ring.
   double* ring = nullptr;
   size_t ring_rows = 0;
   uint64_t rows_enq = 0, rows_landed = 0, rows_consumed = 0;
   std::deque<PendingCopy> pending;
   std::vector<cudaEvent_t> ev_pool;
+  // wire "delta"
+  CompactBuf cbuf[kCompactBufs];
+  unsigned char* cring = nullptr;      // pinned byte ring of compact segments
+  size_t cring_bytes = 0, cring_head = 0;
+  std::deque<HostSeg> hsegs;           // enqueued, not yet released
+  uint64_t rows_expanded = 0;          // rows materialised into `ring` so far (>= rows_consumed)
+  std::vector<double> prev_row;        // [S][d+3] state of the expansion cursor
+  const double* prev_last_dev = nullptr;  // the previous launch's last round of full rows (device)
+  bool force_key = true;               // the next segment must not lean on earlier rows
+  double est_changed_per_round = -1.0; // payload rows per round of recent segments (sizes the copies)
+  uint64_t d2h_bytes = 0;              // bytes handed to the copy engine so far
+  FILE* bin_file = nullptr;            // sink "bin"
   // csv sink
   std::vector<std::string> csv_buf;
   CsvPool csv;
@@ -232,6 +288,12 @@ Settings parse_settings(const char* text) {
     if (g->find("windowRates")) s.windowRates = need(*g, "windowRates", slgpu_json::Value::Bool).b;
     if (g->find("csvThreads")) s.csvThreads = (uint32_t)need_uint(*g, "csvThreads");
     if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
+    if (g->find("wire")) {
+      const std::string& k = need(*g, "wire", slgpu_json::Value::String).str;
+      if (k == "delta") s.wire = WIRE_DELTA;
+      else if (k == "full") s.wire = WIRE_FULL;
+      else throw ConfigError{"gpu.wire must be \"delta\" or \"full\""};
+    }
     if (g->find("rng")) {
       const std::string& r = need(*g, "rng", slgpu_json::Value::String).str;
       if (r == "philox") s.rng = SLGPU_RNG_PHILOX;
@@ -244,7 +306,8 @@ Settings parse_settings(const char* text) {
       else if (k == "device") s.sink = SINK_DEVICE;
       else if (k == "host") s.sink = SINK_HOST;
       else if (k == "csv") s.sink = SINK_CSV;
-      else throw ConfigError{"gpu.sink must be one of none, device, host, csv"};
+      else if (k == "bin") s.sink = SINK_BIN;
+      else throw ConfigError{"gpu.sink must be one of none, device, host, csv, bin"};
     }
   }
   if (s.adaptInterval == 0 || s.maxRoundsPerLaunch == 0) throw ConfigError{"gpu.adaptInterval and gpu.maxRoundsPerLaunch must be positive"};
@@ -284,8 +347,48 @@ cudaEvent_t get_event(slgpu_engine* e) {
   return ev;
 }
 
+inline bool delta_wire(const slgpu_engine* e) {
+  return e->cfg.wire == WIRE_DELTA && (e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV || e->cfg.sink == SINK_BIN);
+}
+
+// wire "delta": has the oldest not-yet-landed segment landed?  Checks the payload count against what the first copy
+// covered and fetches the rest if the estimate was short (rare: the accept rates move slowly).
+slgpu_status land_segment(slgpu_engine* e, HostSeg& hs, bool block, bool* landed) {
+  *landed = false;
+  if (block) CU_TRY(cudaEventSynchronize(hs.ev));
+  else if (cudaEventQuery(hs.ev) != cudaSuccess) return SLGPU_OK;
+  const uint32_t count = ((const uint32_t*)(e->cring + hs.off))[2];
+  if (count > hs.cap_copied && !hs.remainder) {
+    const SegLayout L = seg_layout(hs.n_rounds, e->cfg.nStacks);
+    const size_t from = L.bytes(hs.cap_copied, e->cfg.nDims), to = L.bytes(count, e->cfg.nDims);
+    CU_TRY(cudaMemcpyAsync(e->cring + hs.off + from, hs.dev + from, to - from, cudaMemcpyDeviceToHost, e->drain));
+    CU_TRY(cudaEventRecord(hs.ev, e->drain));
+    e->d2h_bytes += to - from;
+    hs.remainder = true;
+    hs.cap_copied = count;
+    if (!block) return SLGPU_OK;
+    CU_TRY(cudaEventSynchronize(hs.ev));
+  }
+  hs.landed = true;
+  *landed = true;
+  const bool key = ((const uint32_t*)(e->cring + hs.off))[3] != 0;
+  const uint32_t plain_rounds = hs.n_rounds - (key ? 1u : 0u);
+  if (plain_rounds) e->est_changed_per_round = (double)(count - (key ? e->cfg.nStacks : 0u)) / plain_rounds;
+  return SLGPU_OK;
+}
+
 // rows whose D2H copy has completed
 void poll_landed(slgpu_engine* e, bool block) {
+  if (delta_wire(e)) {
+    for (HostSeg& hs : e->hsegs) {
+      if (!hs.landed) {
+        bool ok = false;
+        if (land_segment(e, hs, block, &ok) != SLGPU_OK || !ok) break;
+      }
+      e->rows_landed = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+    }
+    return;
+  }
   while (!e->pending.empty()) {
     PendingCopy& pc = e->pending.front();
     if (block) cudaEventSynchronize(pc.ev);
@@ -296,6 +399,61 @@ void poll_landed(slgpu_engine* e, bool block) {
   }
   if (e->cfg.overwrite && e->rows_landed > e->ring_rows && e->rows_consumed + e->ring_rows < e->rows_landed)
     e->rows_consumed = e->rows_landed - e->ring_rows;
+}
+
+// one compact segment applied to the expansion state; rows != NULL also writes the full (d + 5)-double rows
+void apply_segment(slgpu_engine* e, const HostSeg& hs, double* ring) {
+  const uint32_t S = e->cfg.nStacks, w = e->row_w, wp = w - 2;
+  const SegLayout L = seg_layout(hs.n_rounds, S);
+  const unsigned char* seg = e->cring + hs.off;
+  const uint32_t* base = (const uint32_t*)(seg + L.off_base);
+  const unsigned char* flags = seg + L.off_flags;
+  const double* pay = (const double*)(seg + L.off_payload);
+  if (e->prev_row.size() != (size_t)S * wp) e->prev_row.assign((size_t)S * wp, 0.0);
+  for (uint32_t r = 0; r < hs.n_rounds; ++r) {
+    for (uint32_t c = 0; c < L.n_chunks; ++c) {
+      const double* src = pay + (size_t)base[(size_t)r * L.n_chunks + c] * wp;
+      const uint32_t s1 = std::min(S, (c + 1) * (uint32_t)slgpu_rows::kChunk);
+      for (uint32_t st = c * slgpu_rows::kChunk; st < s1; ++st) {
+        const unsigned f = flags[(size_t)r * S + st];
+        double* pv = e->prev_row.data() + (size_t)st * wp;
+        if (f & 8u) {
+          std::memcpy(pv, src, wp * sizeof(double));
+          src += wp;
+        }
+        if (ring) {
+          double* out = ring + (size_t)((hs.row_begin + (uint64_t)r * S + st) % e->ring_rows) * w;
+          std::memcpy(out, pv, wp * sizeof(double));
+          out[wp] = (double)(f & 1u);
+          out[wp + 1] = (double)((f >> 1) & 3u);
+        }
+      }
+    }
+  }
+}
+
+void release_front_segment(slgpu_engine* e) {
+  HostSeg& hs = e->hsegs.front();
+  e->ev_pool.push_back(hs.ev);
+  e->hsegs.pop_front();
+}
+
+// wire "delta": rebuild the full rows of every landed segment into the (pageable) row ring
+slgpu_status materialise(slgpu_engine* e) {
+  if (!delta_wire(e)) return SLGPU_OK;
+  while (!e->hsegs.empty() && e->hsegs.front().landed) {
+    if (!e->ring) {
+      e->ring = (double*)std::malloc(e->ring_rows * e->row_w * sizeof(double));
+      if (!e->ring) return fail(SLGPU_E_STATE, "out of host memory for the row ring");
+    }
+    const HostSeg& hs = e->hsegs.front();
+    const uint64_t end = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+    if (e->cfg.overwrite && end > e->rows_consumed + e->ring_rows) e->rows_consumed = end - e->ring_rows;
+    apply_segment(e, hs, e->ring);
+    e->rows_expanded = end;
+    release_front_segment(e);
+  }
+  return SLGPU_OK;
 }
 
 // One value as operator<<(ostream&, double) prints it with default flags (precision 6, general): printf's "%g".
@@ -405,10 +563,14 @@ void csv_pool_stop(slgpu_engine* e) {
 // buffers go to the files when they hold 64 MiB together, and at the end (finalise)
 slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
   poll_landed(e, block);
+  {
+    slgpu_status st = materialise(e);
+    if (st != SLGPU_OK) return st;
+  }
   CsvPool& cp = e->csv;
   size_t held = 0;
   for (size_t b : cp.buffered) held += b;
-  const uint64_t r0 = e->rows_consumed, r1 = e->rows_landed;
+  const uint64_t r0 = e->rows_consumed, r1 = delta_wire(e) ? e->rows_expanded : e->rows_landed;
   const bool flush = finalise || held + (r1 - r0) * 12 * e->row_w > (64u << 20);
   if (r0 == r1 && !(flush && held)) return SLGPU_OK;
   if (cp.threads.empty()) {
@@ -426,6 +588,28 @@ slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
   return SLGPU_OK;
 }
 
+// sink "bin": every landed compact segment goes to <outputPath>/chains-<stackOffset>.slgpu as it is -- a 32-byte
+// record header {magic "SLGS", n_rounds, row_begin (u64), bytes (u64), reserved} followed by the segment (header, base,
+// flags, payload[count]).  stateline_b200/binlog.py rebuilds the rows.  This is the sink that keeps up with the GPU:
+// ~50 bytes per cold row instead of ~150 characters of text.
+slgpu_status bin_pump(slgpu_engine* e, bool block, bool finalise) {
+  poll_landed(e, block);
+  while (!e->hsegs.empty() && e->hsegs.front().landed) {
+    const HostSeg& hs = e->hsegs.front();
+    const unsigned char* seg = e->cring + hs.off;
+    const uint32_t count = ((const uint32_t*)seg)[2];
+    const uint64_t bytes = seg_layout(hs.n_rounds, e->cfg.nStacks).bytes(count, e->cfg.nDims);
+    struct { char magic[4]; uint32_t n_rounds; uint64_t row_begin, bytes, reserved; } rec = {{'S', 'L', 'G', 'S'}, hs.n_rounds, hs.row_begin, bytes, 0};
+    if (std::fwrite(&rec, sizeof rec, 1, e->bin_file) != 1 || std::fwrite(seg, 1, bytes, e->bin_file) != bytes)
+      return fail(SLGPU_E_IO, "short write to the binary chain file under " + e->cfg.outputPath);
+    const uint64_t end = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+    e->rows_consumed = e->rows_expanded = end;
+    release_front_segment(e);
+  }
+  if (finalise && std::fflush(e->bin_file) != 0) return fail(SLGPU_E_IO, "cannot flush the binary chain file under " + e->cfg.outputPath);
+  return SLGPU_OK;
+}
+
 // queue the D2H copy of a finished segment into the host ring
 slgpu_status enqueue_copy(slgpu_engine* e, Segment& sg, uint64_t n_rows) {
   CU_TRY(cudaStreamWaitEvent(e->drain, sg.written, 0));
@@ -435,6 +619,7 @@ slgpu_status enqueue_copy(slgpu_engine* e, Segment& sg, uint64_t n_rows) {
     const uint64_t n = std::min<uint64_t>(n_rows - done, e->ring_rows - pos);
     CU_TRY(cudaMemcpyAsync(e->ring + pos * e->row_w, sg.dev + (size_t)done * e->row_w, (size_t)n * e->row_w * sizeof(double),
                            cudaMemcpyDeviceToHost, e->drain));
+    e->d2h_bytes += (size_t)n * e->row_w * sizeof(double);
     done += n;
   }
   CU_TRY(cudaEventRecord(sg.copied, e->drain));
@@ -451,10 +636,96 @@ bool ring_has_room(slgpu_engine* e, uint64_t n_rows) {
   return e->rows_enq + n_rows - e->rows_consumed <= e->ring_rows;
 }
 
+// wire "delta": `bytes` contiguous bytes of the pinned byte ring (segments are released oldest first)
+bool cring_reserve(slgpu_engine* e, size_t bytes, size_t* off) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes > e->cring_bytes) return false;
+  if (e->hsegs.empty()) {
+    e->cring_head = 0;
+  }
+  const size_t tail = e->hsegs.empty() ? 0 : e->hsegs.front().off;
+  const bool wrapped = !e->hsegs.empty() && e->cring_head <= tail;  // head has wrapped behind the oldest segment (or the ring is full)
+  if (!wrapped) {
+    if (e->cring_head + bytes <= e->cring_bytes) {
+      *off = e->cring_head;
+    } else if (!e->hsegs.empty() && bytes <= tail) {
+      *off = 0;
+    } else if (e->hsegs.empty()) {
+      *off = 0;
+    } else {
+      return false;
+    }
+  } else {
+    if (e->cring_head + bytes > tail) return false;
+    *off = e->cring_head;
+  }
+  e->cring_head = *off + bytes;
+  return true;
+}
+
+// wire "delta": compact the launch's rows on the compute stream and queue ONE copy of the compact segment.
+// The copy covers the fixed part and as many payload rows as recent segments needed (+25 %); land_segment fetches the
+// rest in the rare case that was short.  A compact device buffer is reused only after the host has seen its segment
+// land, so that such a late fetch always finds its data.
+slgpu_status enqueue_compact(slgpu_engine* e, const double* rows_dev, uint32_t n_rounds) {
+  const uint32_t S = e->cfg.nStacks, d = e->cfg.nDims;
+  CompactBuf& cb = e->cbuf[e->seg_next % kCompactBufs];
+  for (HostSeg& hs : e->hsegs) {  // the segment that used this buffer last, if it is still in flight
+    if (hs.dev == cb.dev && !hs.landed) {
+      for (HostSeg& h2 : e->hsegs) {  // segments land in order
+        bool ok = false;
+        if (!h2.landed) {
+          slgpu_status st = land_segment(e, h2, true, &ok);
+          if (st != SLGPU_OK) return st;
+        }
+        if (&h2 == &hs) break;
+      }
+      break;
+    }
+  }
+  const SegLayout L = seg_layout(n_rounds, S);
+  const bool key = e->force_key || e->cfg.overwrite || !e->prev_last_dev;
+  CU_TRY(cudaMemsetAsync(cb.dev, 0, 16, e->compute));
+  slgpu_rows::k_compact_rows<<<dim3(L.n_chunks, n_rounds), slgpu_rows::kChunk, 0, e->compute>>>(
+      rows_dev, e->prev_last_dev, S, e->row_w, n_rounds, key ? 1 : 0, cb.dev, L.n_chunks, (uint32_t)L.off_flags, (uint32_t)L.off_payload);
+  CU_TRY(cudaGetLastError());
+  e->launches++;
+  CU_TRY(cudaEventRecord(cb.written, e->compute));
+  const uint32_t capacity = n_rounds * S;
+  uint32_t cap = capacity;
+  if (e->est_changed_per_round >= 0.0) {
+    const double want = e->est_changed_per_round * (n_rounds - (key ? 1 : 0)) * 1.25 + 128.0 + (key ? S : 0);
+    if (want < (double)capacity) cap = (uint32_t)want;
+  }
+  size_t off = 0;
+  while (!cring_reserve(e, L.bytes(capacity, d), &off)) {
+    if (!e->cfg.overwrite || e->hsegs.empty()) return fail(SLGPU_E_FULL, "host ring cannot take the segment: drain first or raise gpu.hostRingRounds");
+    HostSeg& old = e->hsegs.front();  // overwrite: the oldest unconsumed segment makes room (every segment is a key segment)
+    if (!old.landed) CU_TRY(cudaEventSynchronize(old.ev));
+    const uint64_t end = old.row_begin + (uint64_t)old.n_rounds * S;
+    e->rows_landed = std::max(e->rows_landed, end);
+    e->rows_consumed = std::max(e->rows_consumed, end);
+    e->rows_expanded = std::max(e->rows_expanded, end);
+    release_front_segment(e);
+  }
+  CU_TRY(cudaStreamWaitEvent(e->drain, cb.written, 0));
+  CU_TRY(cudaMemcpyAsync(e->cring + off, cb.dev, L.bytes(cap, d), cudaMemcpyDeviceToHost, e->drain));
+  e->d2h_bytes += L.bytes(cap, d);
+  HostSeg hs;
+  hs.off = off; hs.reserved = L.bytes(capacity, d); hs.n_rounds = n_rounds; hs.cap_copied = cap;
+  hs.row_begin = e->rows_enq; hs.dev = cb.dev; hs.ev = get_event(e);
+  CU_TRY(cudaEventRecord(hs.ev, e->drain));
+  e->hsegs.push_back(hs);
+  e->rows_enq += (uint64_t)n_rounds * S;
+  e->prev_last_dev = rows_dev + (size_t)(n_rounds - 1) * S * e->row_w;
+  e->force_key = false;
+  return SLGPU_OK;
+}
+
 // one launch of the plugin's step kernel over [rounds_done, rounds_done + n)
 slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
   const bool emit = e->cfg.sink != SINK_NONE;
-  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV;
+  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV || e->cfg.sink == SINK_BIN;
   const uint64_t n_rows = (uint64_t)n * e->cfg.nStacks;
   Segment& sg = e->seg[e->seg_next % kSegments];
   if (emit) {
@@ -464,6 +735,14 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
         if (st != SLGPU_OK) return st;
         while (!ring_has_room(e, n_rows)) {
           st = csv_pump(e, true, false);
+          if (st != SLGPU_OK) return st;
+        }
+      }
+      if (e->cfg.sink == SINK_BIN) {
+        slgpu_status st = bin_pump(e, false, false);
+        if (st != SLGPU_OK) return st;
+        while (!ring_has_room(e, n_rows)) {
+          st = bin_pump(e, true, false);
           if (st != SLGPU_OK) return st;
         }
       }
@@ -502,8 +781,13 @@ slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
   if (emit) {
     e->rows_emitted += n_rows;
     if (to_host) {
-      CU_TRY(cudaEventRecord(sg.written, e->compute));
-      slgpu_status st = enqueue_copy(e, sg, n_rows);
+      slgpu_status st;
+      if (delta_wire(e)) {
+        st = enqueue_compact(e, sg.dev, n);
+      } else {
+        CU_TRY(cudaEventRecord(sg.written, e->compute));
+        st = enqueue_copy(e, sg, n_rows);
+      }
       if (st != SLGPU_OK) return st;
     }
     e->seg_next++;
@@ -709,7 +993,7 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
     }
     if (cfg.sink != SINK_NONE) {
       const size_t seg_doubles = (size_t)e->seg_rounds * S * e->row_w;
-      const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;
+      const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;  // wire "delta" compares a launch with the previous one: distinct buffers
       for (int i = 0; i < kSegments; ++i) {
         if (i < nseg) {
           TRY_ST(dev_alloc(e, &e->seg[i].dev, seg_doubles));
@@ -720,11 +1004,35 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
         CU_TRY(cudaEventCreateWithFlags(&e->seg[i].copied, cudaEventDisableTiming));
       }
     }
-    if (cfg.sink == SINK_HOST || cfg.sink == SINK_CSV) {
+    if (cfg.sink == SINK_BIN && cfg.wire != WIRE_DELTA) return fail(SLGPU_E_CONFIG, "gpu.sink \"bin\" writes the delta stream: it needs gpu.wire \"delta\"");
+    if (cfg.sink == SINK_HOST || cfg.sink == SINK_CSV || cfg.sink == SINK_BIN) {
       uint64_t rr = cfg.hostRingRounds ? cfg.hostRingRounds : (uint64_t)8 * e->seg_rounds;
       rr = std::max<uint64_t>(rr, (uint64_t)e->seg_rounds + 1);
       e->ring_rows = (size_t)rr * S;
-      CU_TRY(cudaHostAlloc((void**)&e->ring, e->ring_rows * e->row_w * sizeof(double), cudaHostAllocDefault));
+      if (delta_wire(e)) {
+        // compact segments: a pinned byte ring that can hold what the row ring could (a segment reserves its worst case)
+        const size_t maxseg = seg_layout(e->seg_rounds, S).bytes(e->seg_rounds * S, d) + 256;
+        e->cring_bytes = e->ring_rows * e->row_w * sizeof(double) + (size_t)(rr + 4) * 512 + 2 * maxseg;
+        CU_TRY(cudaHostAlloc((void**)&e->cring, e->cring_bytes, cudaHostAllocDefault));
+        for (int i = 0; i < kCompactBufs; ++i) {
+          TRY_ST(dev_alloc(e, &e->cbuf[i].dev, maxseg));
+          CU_TRY(cudaEventCreateWithFlags(&e->cbuf[i].written, cudaEventDisableTiming));
+          CU_TRY(cudaEventCreateWithFlags(&e->cbuf[i].copied, cudaEventDisableTiming));
+        }
+      } else {
+        CU_TRY(cudaHostAlloc((void**)&e->ring, e->ring_rows * e->row_w * sizeof(double), cudaHostAllocDefault));
+      }
+    }
+    if (cfg.sink == SINK_BIN) {
+      mkdir(cfg.outputPath.c_str(), 0777);
+      const std::string path = cfg.outputPath + "/chains-" + std::to_string(cfg.stackOffset) + ".slgpu";
+      e->bin_file = std::fopen(path.c_str(), cfg.append ? "ab" : "wb");
+      if (!e->bin_file) return fail(SLGPU_E_IO, "cannot create " + path);
+      if (!cfg.append || std::ftell(e->bin_file) == 0) {
+        struct { char magic[8]; uint32_t version, n_stacks, n_temps, n_dims, stack_offset, chunk; } fh = {
+            {'S', 'L', 'G', 'P', 'U', 'B', 'I', 'N'}, 1, S, T, d, cfg.stackOffset, (uint32_t)slgpu_rows::kChunk};
+        if (std::fwrite(&fh, sizeof fh, 1, e->bin_file) != 1) return fail(SLGPU_E_IO, "cannot write " + path);
+      }
     }
     if (cfg.sink == SINK_CSV) {
       // CSVChainArrayWriter ctor, db.cpp:27-35: one file per stack, truncated on open
@@ -759,13 +1067,26 @@ void slgpu_destroy(slgpu_engine* e) {
   if (e->compute) cudaStreamSynchronize(e->compute);
   if (e->drain) cudaStreamSynchronize(e->drain);
   if (e->cfg.sink == SINK_CSV) {
-    if (e->initialised && !e->failed && e->ring) csv_pump(e, true, true);
+    if (e->initialised && !e->failed && (e->ring || e->cring)) csv_pump(e, true, true);
     csv_pool_stop(e);
   }
   for (void* p : e->allocs) cudaFree(p);
   for (auto& p : {e->d_rp_z, e->d_rp_umh, e->d_rp_uswap, e->d_rp_xinit})
     if (p) cudaFree(p);
-  if (e->ring) cudaFreeHost(e->ring);
+  if (e->cfg.sink == SINK_BIN && e->bin_file) {
+    if (e->initialised && !e->failed) bin_pump(e, true, true);
+    std::fclose(e->bin_file);
+  }
+  if (e->ring) {
+    if (delta_wire(e)) std::free(e->ring);
+    else cudaFreeHost(e->ring);
+  }
+  if (e->cring) cudaFreeHost(e->cring);
+  for (auto& cb : e->cbuf) {
+    if (cb.written) cudaEventDestroy(cb.written);
+    if (cb.copied) cudaEventDestroy(cb.copied);
+  }
+  for (auto& hs : e->hsegs) cudaEventDestroy(hs.ev);
   for (auto& sg : e->seg) {
     if (sg.written) cudaEventDestroy(sg.written);
     if (sg.copied) cudaEventDestroy(sg.copied);
@@ -814,7 +1135,7 @@ slgpu_status slgpu_init_chains(slgpu_engine* e) {
   if (e->cfg.rng == SLGPU_RNG_REPLAY && !e->cfg.useInitial && !e->d_rp_xinit)
     return fail(SLGPU_E_STATE, "rng \"replay\" needs slgpu_set_replay before slgpu_init_chains");
   const bool emit = e->cfg.sink != SINK_NONE;
-  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV;
+  const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV || e->cfg.sink == SINK_BIN;
   Segment& sg = e->seg[e->seg_next % kSegments];
   e->P.rows_out = emit ? sg.dev : nullptr;
   e->P.round_begin = 0;
@@ -830,8 +1151,14 @@ slgpu_status slgpu_init_chains(slgpu_engine* e) {
   if (emit) {
     e->rows_emitted += e->cfg.nStacks;
     if (to_host) {
-      CU_TRY(cudaEventRecord(sg.written, e->compute));
-      if ((st = enqueue_copy(e, sg, e->cfg.nStacks)) != SLGPU_OK) return st;
+      if (delta_wire(e)) {
+        e->force_key = true;  // the initial rows are everybody's first row
+        e->prev_last_dev = nullptr;
+        if ((st = enqueue_compact(e, sg.dev, 1)) != SLGPU_OK) return st;
+      } else {
+        CU_TRY(cudaEventRecord(sg.written, e->compute));
+        if ((st = enqueue_copy(e, sg, e->cfg.nStacks)) != SLGPU_OK) return st;
+      }
     }
     e->seg_next++;
   }
@@ -875,6 +1202,7 @@ slgpu_status slgpu_sync(slgpu_engine* e) {
   if (st != SLGPU_OK) return st;
   if ((st = sync_all(e)) != SLGPU_OK) return st;
   if (e->cfg.sink == SINK_CSV && e->initialised) return csv_pump(e, true, true);  // every landed row is in its file
+  if (e->cfg.sink == SINK_BIN && e->initialised) return bin_pump(e, true, true);
   return SLGPU_OK;
 }
 
@@ -897,6 +1225,7 @@ slgpu_status slgpu_run(slgpu_engine* e) {
   }
   if ((st = sync_all(e)) != SLGPU_OK) return st;
   if (e->cfg.sink == SINK_CSV) return csv_pump(e, true, true);  // Sampler::flush, sampler.cpp:216-235
+  if (e->cfg.sink == SINK_BIN) return bin_pump(e, true, true);
   return SLGPU_OK;
 }
 
@@ -919,7 +1248,8 @@ slgpu_status slgpu_drain(slgpu_engine* e, double* rows, size_t cap_rows, size_t*
   if (!n_rows || (!rows && cap_rows)) return fail(SLGPU_E_ARG, "rows / n_rows must not be NULL");
   if (e->cfg.sink != SINK_HOST) return fail(SLGPU_E_STATE, "slgpu_drain needs gpu.sink \"host\"");
   poll_landed(e, true);
-  size_t n = (size_t)std::min<uint64_t>(cap_rows, e->rows_landed - e->rows_consumed);
+  if ((st = materialise(e)) != SLGPU_OK) return st;
+  size_t n = (size_t)std::min<uint64_t>(cap_rows, (delta_wire(e) ? e->rows_expanded : e->rows_landed) - e->rows_consumed);
   size_t done = 0;
   while (done < n) {
     const size_t pos = (size_t)((e->rows_consumed + done) % e->ring_rows);
@@ -938,7 +1268,8 @@ slgpu_status slgpu_peek(slgpu_engine* e, const double** span0, size_t* n0, const
   if (!span0 || !n0 || !span1 || !n1) return fail(SLGPU_E_ARG, "span pointers must not be NULL");
   if (e->cfg.sink != SINK_HOST) return fail(SLGPU_E_STATE, "slgpu_peek needs gpu.sink \"host\"");
   poll_landed(e, false);
-  const size_t avail = (size_t)(e->rows_landed - e->rows_consumed);
+  if ((st = materialise(e)) != SLGPU_OK) return st;
+  const size_t avail = (size_t)((delta_wire(e) ? e->rows_expanded : e->rows_landed) - e->rows_consumed);
   const size_t pos = (size_t)(e->rows_consumed % e->ring_rows);
   const size_t first = std::min(avail, e->ring_rows - pos);
   *span0 = e->ring + pos * e->row_w;
@@ -950,10 +1281,52 @@ slgpu_status slgpu_peek(slgpu_engine* e, const double** span0, size_t* n0, const
 
 slgpu_status slgpu_advance(slgpu_engine* e, size_t n_rows) {
   if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
-  if (n_rows > e->rows_landed - e->rows_consumed) return fail(SLGPU_E_ARG, "cannot advance past the landed rows");
+  if (n_rows > (delta_wire(e) ? e->rows_expanded : e->rows_landed) - e->rows_consumed) return fail(SLGPU_E_ARG, "cannot advance past the landed rows");
   e->rows_consumed += n_rows;
   return SLGPU_OK;
 }
+
+slgpu_status slgpu_next_segment(slgpu_engine* e, int block, slgpu_segment* out) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if (!out) return fail(SLGPU_E_ARG, "out must not be NULL");
+  if (!(delta_wire(e) && e->cfg.sink == SINK_HOST)) return fail(SLGPU_E_STATE, "slgpu_next_segment needs gpu.sink \"host\" with gpu.wire \"delta\"");
+  if (e->rows_consumed != e->rows_expanded) return fail(SLGPU_E_STATE, "drain the materialised rows before taking segments");
+  std::memset(out, 0, sizeof *out);
+  if (e->hsegs.empty()) return SLGPU_OK;
+  HostSeg& hs = e->hsegs.front();
+  if (!hs.landed) {
+    bool ok = false;
+    if ((st = land_segment(e, hs, block != 0, &ok)) != SLGPU_OK) return st;
+    if (!ok) return SLGPU_OK;
+  }
+  const SegLayout L = seg_layout(hs.n_rounds, e->cfg.nStacks);
+  const unsigned char* seg = e->cring + hs.off;
+  out->n_rounds = hs.n_rounds;
+  out->n_stacks = e->cfg.nStacks;
+  out->n_chunks = L.n_chunks;
+  out->payload_doubles = e->row_w - 2;
+  out->count = ((const uint32_t*)seg)[2];
+  out->key = ((const uint32_t*)seg)[3];
+  out->row_begin = hs.row_begin;
+  out->base = (const uint32_t*)(seg + L.off_base);
+  out->flags = seg + L.off_flags;
+  out->payload = (const double*)(seg + L.off_payload);
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_release_segment(slgpu_engine* e) {
+  if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
+  if (e->hsegs.empty() || !e->hsegs.front().landed) return fail(SLGPU_E_STATE, "no landed segment to release");
+  const HostSeg& hs = e->hsegs.front();
+  apply_segment(e, hs, nullptr);  // a later slgpu_drain starts from the right rows
+  e->rows_consumed = e->rows_expanded = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+  e->rows_landed = std::max(e->rows_landed, e->rows_consumed);
+  release_front_segment(e);
+  return SLGPU_OK;
+}
+
+uint64_t slgpu_d2h_bytes(const slgpu_engine* e) { return e ? e->d2h_bytes : 0; }
 
 slgpu_status slgpu_timer_start(slgpu_engine* e) {
   slgpu_status st = check_ready(e, false);
@@ -1434,6 +1807,8 @@ slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
   }
   e->rounds_done = h.rounds_done;
   e->initialised = true;
+  e->force_key = true;  // the resumed stream starts with a key segment: the host has no earlier row to lean on
+  e->prev_last_dev = nullptr;
   return SLGPU_OK;
 }
 

@@ -30,7 +30,14 @@ SYMBOLS = [
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
     "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
+    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes",
 ]
+
+
+class _Segment(C.Structure):
+    _fields_ = [("n_rounds", C.c_uint32), ("n_stacks", C.c_uint32), ("n_chunks", C.c_uint32), ("payload_doubles", C.c_uint32),
+                ("count", C.c_uint32), ("key", C.c_uint32), ("row_begin", C.c_uint64), ("base", C.POINTER(C.c_uint32)),
+                ("flags", C.POINTER(C.c_ubyte)), ("payload", _dp)]
 
 BUILTIN_ENTRIES = {
     "demo_gauss": "slgpu_plugin_demo_gauss",
@@ -103,6 +110,10 @@ def lib():
     L.slgpu_format_table.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, _szp]
     L.slgpu_save_state.argtypes = [C.c_void_p, C.c_char_p]
     L.slgpu_load_state.argtypes = [C.c_void_p, C.c_char_p]
+    L.slgpu_next_segment.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Segment)]
+    L.slgpu_release_segment.argtypes = [C.c_void_p]
+    L.slgpu_d2h_bytes.argtypes = [C.c_void_p]
+    L.slgpu_d2h_bytes.restype = C.c_uint64
     _lib = L
     return L
 
@@ -289,6 +300,27 @@ class Engine:
 
     def advance(self, n):
         _check(lib().slgpu_advance(self.h, int(n)))
+
+    def next_segment(self, block=False):
+        """The oldest landed segment of the delta stream (sink "host", wire "delta") as zero-copy numpy views into the
+        pinned ring: dict(n_rounds, row_begin, count, key, base[n_rounds, n_chunks], flags[n_rounds, S],
+        payload[count, d + 3]), or None when nothing has landed.  Release it with release_segment()."""
+        sg = _Segment()
+        _check(lib().slgpu_next_segment(self.h, 1 if block else 0, C.byref(sg)))
+        if sg.n_rounds == 0:
+            return None
+        as_array = np.ctypeslib.as_array
+        return dict(n_rounds=sg.n_rounds, row_begin=sg.row_begin, count=sg.count, key=bool(sg.key),
+                    base=as_array(sg.base, shape=(sg.n_rounds, sg.n_chunks)),
+                    flags=as_array(sg.flags, shape=(sg.n_rounds, sg.n_stacks)),
+                    payload=as_array(sg.payload, shape=(max(sg.count, 1), sg.payload_doubles))[:sg.count])
+
+    def release_segment(self):
+        _check(lib().slgpu_release_segment(self.h))
+
+    @property
+    def d2h_bytes(self):
+        return int(lib().slgpu_d2h_bytes(self.h))
 
     # ---- inspection (same shapes as oracle.Sampler)
     def last_rows(self):
