@@ -25,16 +25,30 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "config3"
 ROUNDS_PER_STEP = 10  # = swapInterval: launches are cut at adapt points
-# algorithmic fp64 flops per chain step, SURVEY.md 8(d) closed form at d=20, J=10, a=0.234, T=8
-FLOPS_PER_CHAIN_STEP = 1330.0
+STEADY_ROUNDS = 5000  # rounds behind the steady-state arm (the accept rates and the ladder have settled by then)
+# likelihood flops per chain step of the five workloads
+F_LIK = {"config1": 24.0, "config2": 12.0, "config3": 120.0, "config4": 10300.0, "config5": 588.0}
+
+
+def flops_per_chain_step(d, T, f_lik, a):
+    """SURVEY.md 8(d) closed form with the MEASURED mean accept rate a (the shaper update only runs on an accept):
+    F = d(d+1) + 6d + F_lik + 226 + a (d(d+1)/2 + 3d(d-1) + d(d+1) + 4d) + 6d/T."""
+    return d * (d + 1) + 6 * d + f_lik + 226 + a * (d * (d + 1) / 2 + 3 * d * (d - 1) + d * (d + 1) + 4 * d) + 6 * d / T
 
 
 def algorithmic_bytes_per_chain_step(d, T, K):
-    """state (d + d(d+1)/2 + 6) doubles loaded+stored once per launch of K rounds, plus
-    the cold row (d+5 doubles) written once per cold-chain step."""
+    """SURVEY.md 8(d), factors on chip for a launch (d <= 32): state (d + d(d+1)/2 + 6) doubles loaded+stored once per
+    launch of K rounds, plus the cold row (d+5 doubles) written once per cold-chain step."""
     state = (d + d * (d + 1) // 2 + 6) * 8 * 2 / K
     row = (d + 5) * 8 / T
     return state + row
+
+
+def streamed_bytes_per_chain_step(d, T, a):
+    """SURVEY.md 8(d), factors streamed from HBM every round (d > 32): d(d+1)/2 doubles read per step, read and written
+    again on an accept, plus the state vector and the cold row."""
+    nL = d * (d + 1) // 2
+    return nL * 8 * (1 + 2 * a) + 2 * d * 8 + (d + 5) * 8 / T
 
 
 class ClockSampler(threading.Thread):
@@ -170,12 +184,12 @@ def cpu_baseline_reference(budget_s):
     return steps / secs, cores, REF_SAMPLE % (cores, REF_STACKS_PER_PROC, 8, rounds, "")
 
 
-def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
+def cpu_baseline_full(budget_s=8.0, stacks=8, attempts=4):
     """The reference AS SHIPPED: stateline::ServerWrapper + (nproc - 1) stateline::WorkerWrapper over real ZeroMQ sockets
     (oracle/_ref/ref_full: every reference source unmodified, oracle/Makefile.full), on `stacks` stacks x 8 temperatures
-    of config #3.  Returns (chain-steps/s, cores, sample) or None when the binary is absent.  The reference occasionally
-    stalls at start-up (the workers' hello is never registered: about one run in ten here; not investigated further): a run that exceeds its time limit is killed and retried once; the leg
-    gives up (raises) after that, so it can add at most about a minute to a bench run."""
+    of config #3.  Returns (chain-steps/s, cores, sample) or None when the binary is absent.  A run that exceeds its time
+    limit (the reference's own start-up handshake can lose a worker's HELLO) is killed and retried; the leg raises after
+    `attempts` tries, so it adds a bounded time to a bench run."""
     import socket
     import subprocess
     import tempfile
@@ -198,6 +212,7 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
     n_workers = max(1, cores - 1)
     tmp = tempfile.mkdtemp(prefix="slfull_")
     np.asarray(w["oracle_params"], dtype=np.float64).tofile(os.path.join(tmp, "params.bin"))
+    startup = 0.3 + 0.05 * n_workers  # the harness's own sleeps while it brings the workers up (oracle/ref_full.cpp)
 
     def run(rounds, limit):
         cfg = {"nStacks": w["S"], "nTemperatures": w["T"], "nSamplesTotal": w["S"] * rounds, "swapInterval": w["swapInterval"],
@@ -205,7 +220,7 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
                "optimalSwapRate": w["optSwap"], "useInitial": False, "min": list(w["mn"]), "max": list(w["mx"])}
         with open(os.path.join(tmp, "cfg.json"), "w") as f:
             json.dump(cfg, f)
-        for _ in range(2):
+        for _ in range(attempts):
             with socket.socket() as sk:  # a free port for the delegator
                 sk.bind(("127.0.0.1", 0))
                 port = sk.getsockname()[1]
@@ -214,22 +229,27 @@ def cpu_baseline_full(budget_s=8.0, stacks=8, timeout_s=20.0):
                                  stderr=subprocess.DEVNULL, text=True, cwd=tmp)
             try:
                 out, _ = p.communicate(timeout=limit)
-                secs = float(out.split()[0])
-                return secs
+                return float(out.split()[0])
             except Exception:
                 p.kill()
                 p.wait()
-        raise RuntimeError("the reference's server + workers did not finish")
+        raise RuntimeError("the reference's server + workers did not finish in %d attempts" % attempts)
 
-    startup = 0.3 + 0.05 * n_workers  # the harness's own sleeps while it brings the workers up (oracle/ref_full.cpp)
-    t_small = run(20, timeout_s)
-    per_round = max((t_small - startup) / 20, 1e-4)
-    rounds = int(max(20, min(2000, budget_s / per_round)))
-    secs = run(rounds, max(timeout_s, 3.0 * budget_s)) - startup
+    try:
+        # The server samples from the moment the first worker has said hello, i.e. while the harness is still bringing
+        # the others up: a sample has to be several times longer than that start-up for "seconds - start-up" to mean
+        # anything.  Grow the run until the work part is at least ~40 % of the budget, then take that run.
+        rounds, secs = 200, 0.0
+        for _ in range(6):
+            secs = run(rounds, startup + 6.0 * budget_s + 10.0) - startup
+            if secs >= 0.4 * budget_s or rounds >= 20000:
+                break
+            rounds = int(rounds * min(10.0, max(1.5, 0.7 * budget_s / max(secs, 0.05))))
+    finally:
+        for f in os.listdir(tmp):
+            os.unlink(os.path.join(tmp, f))
+        os.rmdir(tmp)
     steps = w["S"] * w["T"] * rounds
-    for f in os.listdir(tmp):
-        os.unlink(os.path.join(tmp, f))
-    os.rmdir(tmp)
     return steps / secs, n_workers + 1, (
         "%d stacks x %d temps of config #3, %d rounds (%d chain steps): the reference as shipped -- ServerWrapper + %d "
         "WorkerWrapper over ZeroMQ (oracle/_ref/ref_full, all reference sources unmodified), chain initialisation included"
@@ -256,10 +276,17 @@ def ess_geyer(x):
     return float(n / tau)
 
 
-def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000):
-    """ESS per cold-chain sample (min over dims, mean over stacks) from a side run of the same workload
-    with fewer stacks; multiplied by cold samples/s it gives ESS/s."""
+def _ess_of_rows(rows, d):
+    """rows [rounds, stacks, d + 5] of cold chains -> ESS per cold sample: min over dims, mean over stacks."""
     import numpy as np
+    rounds, stacks = rows.shape[0], rows.shape[1]
+    per_stack = [min(ess_geyer(rows[:, s, i]) for i in range(d)) for s in range(stacks)]
+    return float(np.mean(per_stack)) / rounds
+
+
+def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000):
+    """GPU arm: ESS per cold-chain sample from a side run of the same workload with fewer stacks; multiplied by cold
+    samples/s it gives ESS/s."""
     from stateline_b200 import Engine, configs
     w = configs.workload(WORKLOAD, S=stacks)
     cfg = configs.engine_config(w, sink="host", device=device, hostRingRounds=rounds + 16, seed=99)
@@ -270,8 +297,38 @@ def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000):
         e.drain()
         e.step_rounds(rounds)
         rows = e.drain().reshape(rounds, stacks, w["d"] + 5)
-    per_stack = [min(ess_geyer(rows[:, s, i]) for i in range(w["d"])) for s in range(stacks)]
-    return float(np.mean(per_stack)) / rounds
+    return _ess_of_rows(rows, w["d"])
+
+
+def ess_per_cold_sample_reference(stacks=16, warm=1000, rounds=3000):
+    """CPU arm: the same estimator on the cold rows the reference's own object code (oracle/_ref) produced."""
+    import tempfile
+    import numpy as np
+    from oracle import ref as R
+    from stateline_b200 import configs
+    w = configs.workload(WORKLOAD, S=stacks)
+    x_init = np.random.default_rng(7).uniform(-1.0, 1.0, (w["S"] * w["T"], w["d"]))
+    out = tempfile.mkdtemp(prefix="slref_ess_")
+    run = R.RefRun(w["S"], w["T"], w["J"], w["swapInterval"], w["optAccept"], w["optSwap"], w["mn"], w["mx"],
+                   w["oracle_target"], x_init, out, target_params=w["oracle_params"], seed=99, max_rounds=0)
+    try:
+        run.run_rounds(warm + rounds)
+        rows = np.stack([run.cold_rows(s)[-rounds:] for s in range(stacks)], axis=1)
+    finally:
+        run.close()
+        for f in os.listdir(out):
+            os.unlink(os.path.join(out, f))
+        os.rmdir(out)
+    return _ess_of_rows(rows, w["d"])
+
+
+def reference_config(cores, T, d, J):
+    """What the reference arm actually runs: a bounded sample of the workload, one server per host core."""
+    return {"workload": "config3: 20-D Gaussian factorised over 10 job types -- bounded sample: %d independent stateline "
+                        "servers x %d stacks x %d temperatures (the GPU arm runs 8192 stacks x %d per GPU; the cost per "
+                        "chain step does not grow with the stack count)" % (cores, REF_STACKS_PER_PROC, T, T),
+            "servers": cores, "stacks_per_server": REF_STACKS_PER_PROC, "stacks_total": cores * REF_STACKS_PER_PROC,
+            "temperatures": T, "dims": d, "job_types": J, "swap_interval": 10, "rng": "the reference's own mt19937 streams"}
 
 
 def run_reference_ref(args):
@@ -301,14 +358,22 @@ def run_reference_ref(args):
             extra["full_server_workers"] = {"value": full[0], "cores": full[1], "kind": "reference", "sample": full[2]}
     except Exception as e:
         sys.stderr.write("reference server + workers leg failed (%r)\n" % (e,))
-    _emit(json.dumps({
+    out = {
         "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": bench_config(w["T"], w["d"], w["J"], 8192),
+        "config": reference_config(cores, w["T"], w["d"], w["J"]),
         "cpu_baseline": dict({"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "reference", "sample": sample}, **extra),
         "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if not args.no_ess:
+        try:
+            eps = ess_per_cold_sample_reference()
+            out["ess"] = {"ess_per_cold_sample": eps, "ess_per_sec": eps * value / w["T"],
+                          "estimator": "Geyer initial positive sequence, min over dims, mean over 16 stacks of a side run of the reference's own code"}
+        except Exception as e:
+            sys.stderr.write("reference ESS leg failed (%r)\n" % (e,))
+    _emit(json.dumps(out))
 
 
 def run_reference(args, rank, world):
@@ -346,7 +411,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": bench_config(w["T"], w["d"], w["J"], 8192),
+        "config": {"workload": "config3: 20-D Gaussian factorised over 10 job types -- bounded sample: one server, %d stacks x %d "
+                               "temperatures, %d worker threads (oracle port)" % (stacks, w["T"], n_workers),
+                   "stacks_total": stacks, "temperatures": w["T"], "dims": w["d"], "job_types": w["J"], "swap_interval": 10},
         "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": n_workers + 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -379,6 +446,65 @@ def _emit(line):
     out.flush()
 
 
+def plugin_digest():
+    """Source hash of the built likelihood plugin (stateline_b200/build.py): ties a stored ncu traffic figure to the
+    kernels it was measured on."""
+    try:
+        from stateline_b200 import build
+        return open(build.TARGETS_SO + ".srchash").read().strip()[:16]
+    except Exception:
+        return None
+
+
+def timed_steps(e, K, R):
+    """K steps of R rounds on engine e: (ms, step-kernel ms, step-kernel launches, accept rate of the region per tier,
+    kernel launches)."""
+    import numpy as np
+    c0 = e.counters()
+    l0 = e.launch_count
+    e.timer_start()
+    for _ in range(K):
+        e.step_rounds(R)
+    ms = e.timer_stop()
+    kms, kn = e.timer_step_kernel()
+    e.sync()
+    c1 = e.counters()
+    T = e.T
+    acc = (c1["accepts"].astype(np.float64) - c0["accepts"]).reshape(-1, T).mean(0) / (K * R)
+    return ms, kms, kn, acc, e.launch_count - l0
+
+
+def side_config(name, S, local_rank, peaks, fp64_peak, steps=12, warm_rounds=199):
+    """A parity-test configuration of BASELINE.json (#4, #5) timed on the device: not the bench line, but the only place
+    the driver sees the d > 32 kernel."""
+    import numpy as np
+    from stateline_b200 import Engine, configs
+    w = configs.workload(name, S=S)
+    d, T, R = w["d"], w["T"], ROUNDS_PER_STEP
+    cfg = configs.engine_config(w, sink="device", device=local_rank, seed=1234)
+    with Engine(cfg, plugin=w["plugin"], payload=w["payload"]) as e:
+        e.init_chains()
+        e.step_rounds(warm_rounds)
+        e.sync()
+        ms, kms, kn, acc, _ = timed_steps(e, steps, R)
+    a = float(np.mean(acc))
+    chain_steps = w["S"] * T * steps * R
+    launch_ms = kms / max(kn, 1)
+    per_launch = w["S"] * T * R
+    bpcs = streamed_bytes_per_chain_step(d, T, a) if d > 32 else algorithmic_bytes_per_chain_step(d, T, R)
+    gbs = bpcs * per_launch / (launch_ms * 1e-3) / 1e9
+    fl = flops_per_chain_step(d, T, F_LIK[name], a)
+    tf = fl * per_launch / (launch_ms * 1e-3) / 1e12
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    return {"workload": "%s: d=%d, %d stacks x %d temperatures" % (name, d, w["S"], T), "value": chain_steps / (ms * 1e-3),
+            "unit": "chain-steps/s", "steps": steps, "rounds_after_init": warm_rounds, "ms_per_step": ms / steps,
+            "kernel": "pt_step_warp_kernel" if d > 32 else "pt_step_fast_kernel", "launch_ms": launch_ms, "accept_rate_mean": a,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "bytes_per_chain_step": bpcs,
+                         "bytes_model": "nL*8*(1+2a) + 2d*8 + (d+5)*8/T (factors streamed every round)" if d > 32 else "SURVEY 8(d), factors once per launch",
+                         "fp64": {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "flops_per_chain_step": fl}}}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -389,6 +515,7 @@ def main():
     ap.add_argument("--stacks", type=int, default=8192, help="stacks per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the steady-state arm, configs #4 / #5 and the strong-scaling arm")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port (server + N worker threads) even when oracle/_ref exists")
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU seconds the whole run is sized for")
@@ -429,12 +556,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
     w = configs.workload(WORKLOAD, S=args.stacks)
     S, T, d, J = w["S"], w["T"], w["d"], w["J"]
     K, W, R = args.steps, args.warmup, ROUNDS_PER_STEP
     chain_steps = world * S * T * K * R
+    per_launch = S * T * R
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    def roofline_of(launch_ms, a_mean, fp64_peak):
+        fl = flops_per_chain_step(d, T, F_LIK[WORKLOAD], a_mean)
+        tf = fl * per_launch / (launch_ms * 1e-3) / 1e12
+        alg = algorithmic_bytes_per_chain_step(d, T, R) * per_launch
+        gbs = alg / (launch_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg, "chain_steps_per_launch": per_launch,
+                "bytes_per_chain_step": algorithmic_bytes_per_chain_step(d, T, R),
+                "fp64": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                         "flops_per_chain_step": fl, "accept_rate_used": a_mean,
+                         "peak_source": "measured live: register-resident DFMA loop (slgpu_measure_fp64_peak)"}}
 
     # ---- device-resident run: rows go to the HBM ring only
+    steady = None
     cfg = configs.engine_config(w, sink="device", device=local_rank, stackOffset=rank * S, seed=1234)
     with Engine(cfg, plugin=w["plugin"], payload=w["payload"]) as e:
         e.init_chains()
@@ -443,16 +598,9 @@ def main():
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        l0 = e.launch_count
-        e.timer_start()
-        for _ in range(K):
-            e.step_rounds(R)
-        ms = e.timer_stop()
-        step_kernel_ms, step_kernel_n = e.timer_step_kernel()
-        e.sync()
+        ms, step_kernel_ms, step_kernel_n, acc_tiers, launches = timed_steps(e, K, R)
         barrier()
         clocks = sampler.finish()
-        launches = e.launch_count - l0
         ms = max_over_ranks(ms)
         summary = e.summary() if rank == 0 else None
         rhat_local = e.rhat_stage1()
@@ -469,80 +617,151 @@ def main():
             b_part, w_part = t[:d].cpu().numpy(), t[d:].cpu().numpy()
         from stateline_b200 import rhat_finish
         rhat = rhat_finish(b_part, w_part, ns, nn)
+        # ---- steady state: the same engine STEADY_ROUNDS rounds later (rank 0 reports; every rank runs it so that the
+        # GPUs of a multi-GPU line stay in step)
+        if not args.no_side:
+            done = e.rounds_done
+            e.step_rounds(STEADY_ROUNDS + (R - (done + STEADY_ROUNDS + 1) % R) % R)  # next launch starts a swap interval
+            e.sync()
+            barrier()
+            Ks = max(10, min(K, 50))
+            s_ms, s_kms, s_kn, s_acc, _ = timed_steps(e, Ks, R)
+            s_ms = max_over_ranks(s_ms)
+            steady = (s_ms, s_kms, s_kn, s_acc, Ks, e.rounds_done)
     value = chain_steps / (ms * 1e-3)
 
-    # ---- end to end: same rounds through the C-ABI with every cold row copied to pinned host memory
-    cfg = configs.engine_config(w, sink="host", overwrite=True, device=local_rank, stackOffset=rank * S, seed=1234,
-                                hostRingRounds=16 * R)
+    # ---- end to end: same rounds through the C-ABI with the cold rows delivered to pinned host memory as the delta
+    # stream (gpu.wire "delta") and taken by the host segment by segment
+    cfg = configs.engine_config(w, sink="host", device=local_rank, stackOffset=rank * S, seed=1234, hostRingRounds=16 * R)
     with Engine(cfg, plugin=w["plugin"], payload=w["payload"]) as e:
         e.init_chains()
-        e.step_rounds(W * R - 1)
-        e.sync()
+        left = W * R - 1
+        while left:  # warm-up: its rows are taken and dropped, the ring holds 16 steps
+            n = min(left, 8 * R)
+            e.step_rounds(n)
+            left -= n
+            e.sync()
+            while e.next_segment(block=True) is not None:
+                e.release_segment()
         barrier()
-        t0 = time.perf_counter()
+        b0 = e.d2h_bytes
         rows0 = e.rows_emitted
+        n_accept = 0
+        n_changed = 0
+        n_rows_seen = 0
+        last_energy = 0.0
+        t0 = time.perf_counter()
+        in_flight = 0
         for _ in range(K):
             e.step_rounds(R)
+            in_flight += 1
+            while True:  # take what has landed; never run more than 8 steps ahead of the rows (the ring holds 16)
+                sg = e.next_segment(block=in_flight >= 8)
+                if sg is None:
+                    break
+                n_accept += int(np.count_nonzero(sg["flags"] & 1))
+                n_changed += sg["count"]
+                n_rows_seen += sg["flags"].size
+                e.release_segment()
+                in_flight -= 1
+        t_enq = time.perf_counter()
         e.sync()                  # includes the D2H copies of the last segments
-        spans = e.peek()          # the result of the last step, read on the host
-        last = spans[-1][-S:] if spans else np.zeros((0, d + 5))  # the rows of the last round: the result the host reads
-        checksum = float(last[:, d].sum())
+        while True:
+            sg = e.next_segment(block=True)
+            if sg is None:
+                break
+            n_accept += int(np.count_nonzero(sg["flags"] & 1))
+            n_changed += sg["count"]
+            n_rows_seen += sg["flags"].size
+            last_energy = float(sg["payload"][:, d].sum())  # the result of the last step, read on the host
+            e.release_segment()
         t1 = time.perf_counter()
         barrier()
         e2e_s = max_over_ranks(t1 - t0)
         rows = e.rows_emitted - rows0
+        d2h_per_step = (e.d2h_bytes - b0) // K
+        assert n_rows_seen == rows, (n_rows_seen, rows)
     e2e_value = chain_steps / e2e_s
-    d2h_per_step = rows * (d + 5) * 8 // K
+
+    # ---- strong scaling (N > 1): the SAME total number of stacks as the 1-GPU line, split over the ranks
+    strong = None
+    if world > 1 and not args.no_side:
+        from stateline_b200.dist import shard_stacks
+        off, n_local = shard_stacks(args.stacks, rank, world)
+        ws = configs.workload(WORKLOAD, S=n_local)
+        cfg = configs.engine_config(ws, sink="device", device=local_rank, stackOffset=off, seed=1234)
+        with Engine(cfg, plugin=ws["plugin"], payload=ws["payload"]) as e:
+            e.init_chains()
+            e.step_rounds(W * R - 1)
+            e.sync()
+            barrier()
+            s2_ms, _, _, _, _ = timed_steps(e, K, R)
+            barrier()
+            s2_ms = max_over_ranks(s2_ms)
+        strong = {"value": args.stacks * T * K * R / (s2_ms * 1e-3), "unit": "chain-steps/s", "stacks_total": args.stacks,
+                  "stacks_per_gpu": n_local, "ms_per_step": s2_ms / K, "scaling": "strong"}
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (pt_step): fp64 pipe, plus the HBM view
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # ---- roofline of the dominant kernel (pt_step): HBM view (algorithmic bytes) and the fp64 pipe view
     fp64_peak = measure_fp64_peak(local_rank)
-    # the dominant kernel is pt_step (one launch per step); its launches carry their own event pairs
     step_launch_ms = step_kernel_ms / max(step_kernel_n, 1)
-    per_gpu_steps_per_launch = S * T * R
-    achieved_tf = FLOPS_PER_CHAIN_STEP * per_gpu_steps_per_launch / (step_launch_ms * 1e-3) / 1e12
-    alg_bytes = algorithmic_bytes_per_chain_step(d, T, R) * per_gpu_steps_per_launch
-    achieved_gbs = alg_bytes / (step_launch_ms * 1e-3) / 1e9
-    traffic = None
+    a_mean = float(np.mean(acc_tiers))
+    roofline = roofline_of(step_launch_ms, a_mean, fp64_peak)
+    traffic, traffic_note = None, "no ncu capture of this build under profiles/"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "pt_step_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "pt_step_traffic.json")))
+        if tj.get("plugin_digest") == plugin_digest():
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = "ncu --set full of this build (profiles/pt_step_traffic.json: %s)" % tj.get("source", "")
+        else:
+            traffic_note = "profiles/pt_step_traffic.json was measured on another build of the kernels (digest %s, this build %s): not reported" % (
+                tj.get("plugin_digest"), plugin_digest())
     except Exception:
         pass
-    roofline = {
-        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-        "traffic": traffic, "peak_source": hbm_src, "kernel": "pt_step_fast_kernel<GaussFact,20,128>",
-        "launch_ms": step_launch_ms, "launches_timed": int(step_kernel_n), "share_of_step": step_kernel_ms / ms,
-        "algorithmic_bytes_per_launch": alg_bytes, "chain_steps_per_launch": per_gpu_steps_per_launch,
-        "bytes_per_chain_step": algorithmic_bytes_per_chain_step(d, T, R),
-        "note": "latency-bound in round 1: neither roof is close (DESIGN.md section 5, profiles/README.md)",
-        "fp64": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                 "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
-                 "peak_source": "measured live: register-resident DFMA loop (slgpu_measure_fp64_peak)"},
-    }
+    roofline.update({
+        "traffic": traffic, "traffic_source": traffic_note, "peak_source": hbm_src, "kernel": "pt_step_fast_kernel<GaussFact,20,128>",
+        "launches_timed": int(step_kernel_n), "share_of_step": step_kernel_ms / ms,
+        "note": "latency-bound: fp64 dependent-issue latency (~16 cycles) times the serial chains of the step; neither roof is close (DESIGN.md section 5, profiles/README.md)"})
 
     out = {
         "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": bench_config(T, d, J, S), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h_per_step),
-                "note": "inputs are the resident chain state and on-device Philox draws: nothing to upload per step; every cold-chain row is copied D2H to pinned memory inside the timed region",
-                "checksum": checksum, "host_cpus_bound": (len(bound_cpus) if bound_cpus else None)},
+                "full_row_bytes_per_step": int(rows * (d + 5) * 8 // K),
+                "note": "inputs are the resident chain state and on-device Philox draws: nothing to upload per step; the cold rows "
+                        "reach pinned host memory as the delta stream (flag byte per row + the d+3 doubles of the rows whose cold "
+                        "state changed; the host can rebuild every row exactly) inside the timed region; the host reads every flag "
+                        "byte of every segment and the energy column of the last segment",
+                "rows": int(rows), "rows_changed": int(n_changed), "accepted_flags_seen": int(n_accept), "checksum": last_energy,
+                "host_loop_ms": {"enqueue_and_take": 1e3 * (t_enq - t0), "final_sync_and_take": 1e3 * (t1 - t_enq)},
+                "host_cpus_bound": (len(bound_cpus) if bound_cpus else None)},
         "gpu_launches": int(launches), "roofline": roofline,
         "job_evals_per_sec": value * J, "cold_samples_per_sec": value / T,
         "diagnostics": {"rhat_mean": float(np.mean(rhat)), "rhat_max": float(np.max(rhat)),
-                        "accept_rate": summary["accept_rate"], "swap_rate": summary["swap_rate"]},
+                        "accept_rate": summary["accept_rate"], "swap_rate": summary["swap_rate"],
+                        "accept_rate_timed_region": [float(v) for v in acc_tiers]},
+        "phase": "transient: the timed region starts %d rounds after initialisation (hot tiers still at the sigma cap)" % (W * R),
     }
+    if steady:
+        s_ms, s_kms, s_kn, s_acc, Ks, s_rounds = steady
+        out["steady_state"] = {
+            "value": world * S * T * Ks * R / (s_ms * 1e-3), "unit": "chain-steps/s", "steps": Ks, "ms_per_step": s_ms / Ks,
+            "rounds_after_init": int(s_rounds), "accept_rate": [float(v) for v in s_acc],
+            "roofline": roofline_of(s_kms / max(s_kn, 1), float(np.mean(s_acc)), fp64_peak)}
+    if strong:
+        out["strong_scaling"] = strong
+    if not args.no_side and world == 1:
+        out["configs"] = {}
+        for name, Sside in (("config4", 1024), ("config5", 8192)):
+            try:
+                out["configs"][name] = side_config(name, Sside, local_rank, peaks, fp64_peak)
+            except Exception as ex:
+                sys.stderr.write("side config %s failed (%r)\n" % (name, ex))
     if not args.no_ess:
         eps = ess_per_cold_sample(local_rank)
         out["ess"] = {"ess_per_cold_sample": eps, "ess_per_sec": eps * value / T,
@@ -556,6 +775,10 @@ def main():
             try:
                 v, ncores, sample = cpu_baseline_reference(args.cpu_budget)
                 base = {"value": v, "unit": "chain-steps/s", "cores": ncores, "kind": "reference", "sample": sample}
+                if not args.no_ess:
+                    eps_ref = ess_per_cold_sample_reference()
+                    base["ess_per_cold_sample"] = eps_ref
+                    base["ess_per_sec"] = eps_ref * v / T
             except Exception as e:
                 sys.stderr.write("oracle/_ref baseline failed (%r): using the oracle port\n" % (e,))
         # the oracle port in the reference's deployment shape: one server, N worker threads, FIFO job farm, %f wire text

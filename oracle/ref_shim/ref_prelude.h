@@ -52,7 +52,12 @@ using slref::logged_normal;
 using slref::logged_uniform;
 }  // namespace std
 
+/* comms/socket.cpp draws its ZeroMQ identity from random_device (socket.cpp:188-198): pinned, every worker socket of a
+ * process would get the same identity and the delegator's ROUTER would talk to the first one only.  That translation
+ * unit is compiled with -DSLREF_REAL_RANDOM_DEVICE (oracle/Makefile.full). */
+#ifndef SLREF_REAL_RANDOM_DEVICE
 #define random_device fixed_random_device
+#endif
 #define normal_distribution logged_normal
 #define uniform_real_distribution logged_uniform
 #endif
