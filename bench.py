@@ -505,6 +505,76 @@ def side_config(name, S, local_rank, peaks, fp64_peak, steps=12, warm_rounds=199
                          "fp64": {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "flops_per_chain_step": fl}}}
 
 
+def run_group(args):
+    """python bench.py --gpus N WITHOUT torchrun: one process drives the N devices through slgpu_group_* (the C++ host's
+    own multi-GPU path, include/slgpu.h) -- the shape of one `stateline -c cfg` server process.  Same workload per GPU as
+    the torchrun line; `value` from the engines' own CUDA-event timers (max over devices), `e2e` by the wall clock with
+    the delta stream taken per device."""
+    import numpy as np
+    import torch
+    from stateline_b200 import EngineGroup, build, configs
+    build.build_all()
+    if torch.cuda.device_count() < args.gpus:
+        raise SystemExit("bench.py --gpus %d: only %d CUDA devices" % (args.gpus, torch.cuda.device_count()))
+    N, K, W, R = args.gpus, args.steps, max(args.warmup, 3), ROUNDS_PER_STEP
+    w = configs.workload(WORKLOAD, S=args.stacks * N)
+    T, d, J = w["T"], w["d"], w["J"]
+    chain_steps = w["S"] * T * K * R
+    cfg = configs.engine_config(w, sink="device", seed=1234)
+    with EngineGroup(cfg, plugin=w["plugin"], payload=w["payload"], devices=N) as g:
+        g.init_chains()
+        g.step_rounds(W * R - 1)
+        g.sync()
+        for e in g.engines:
+            e.timer_start()
+        for _ in range(K):
+            g.step_rounds(R)
+        ms = max(e.timer_stop() for e in g.engines)
+        g.sync()
+        rhat = g.rhat()
+    cfg = configs.engine_config(w, sink="host", seed=1234, hostRingRounds=16 * R)
+    with EngineGroup(cfg, plugin=w["plugin"], payload=w["payload"], devices=N) as g:
+        g.init_chains()
+        left = W * R - 1
+        while left:
+            n = min(left, 8 * R)
+            g.step_rounds(n)
+            left -= n
+            g.sync()
+            for e in g.engines:
+                while e.next_segment(block=True) is not None:
+                    e.release_segment()
+        b0 = sum(e.d2h_bytes for e in g.engines)
+        seen = 0
+        t0 = time.perf_counter()
+        for k in range(K):
+            g.step_rounds(R)
+            for e in g.engines:
+                while True:
+                    sg = e.next_segment(block=(k % 8 == 7))
+                    if sg is None:
+                        break
+                    seen += int(np.count_nonzero(sg["flags"] & 1))
+                    e.release_segment()
+        g.sync()
+        for e in g.engines:
+            while True:
+                sg = e.next_segment(block=True)
+                if sg is None:
+                    break
+                seen += int(np.count_nonzero(sg["flags"] & 1))
+                e.release_segment()
+        e2e_s = time.perf_counter() - t0
+        d2h = (sum(e.d2h_bytes for e in g.engines) - b0) // K
+    _emit(json.dumps({
+        "metric": "chain_steps_per_sec", "value": chain_steps / (ms * 1e-3), "unit": "chain-steps/s", "n_gpus": N, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": bench_config(T, d, J, args.stacks), "launcher": "single process, slgpu_group (no torchrun)",
+        "e2e": {"value": chain_steps / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                "accepted_flags_seen": seen},
+        "diagnostics": {"rhat_mean": float(np.mean(rhat)), "rhat_max": float(np.max(rhat))}}))
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -528,6 +598,8 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        return run_group(args)  # not under torchrun: the single-process multi-GPU host
 
     import numpy as np
     import torch

@@ -189,6 +189,32 @@ slgpu_status slgpu_format_table(slgpu_engine* e, char* out, size_t cap, size_t* 
 slgpu_status slgpu_save_state(slgpu_engine* e, const char* path);
 slgpu_status slgpu_load_state(slgpu_engine* e, const char* path);
 
+/* ---- several GPUs, one process.  The reference is ONE `stateline -c cfg` process that owns the whole run
+ * (src/bin/stateline.cpp:52-90, src/app/serverwrapper.cpp:44-138); a group does that for several devices.  The stacks of
+ * the config are sharded contiguously over the devices (devices = NULL: gpu.device, gpu.device + 1, ... n_devices of them,
+ * 0 = all visible; or an explicit list, which may name a device more than once), every shard is an engine with its own
+ * tier models and gpu.stackOffset (csv files and Philox streams keep the global stack index), one host thread per device
+ * serves each call below, and there is no traffic between the devices in the step loop.  slgpu_group_run applies the
+ * reference's stop rule to the total (serverwrapper.cpp:100-107); slgpu_group_rhat is EPSRDiagnostic::rHat over all
+ * stacks of all devices (the sums of slgpu_rhat_stage1 / 2 added up in this process).  Everything per engine (drain,
+ * counters, table, ...) goes through slgpu_group_engine(g, i). ---- */
+typedef struct slgpu_group slgpu_group;
+slgpu_status slgpu_group_create(const char* config_json, const char* plugin_path, const char* plugin_entry, const void* payload,
+                                size_t payload_bytes, const int* devices, int n_devices, slgpu_group** out);
+void slgpu_group_destroy(slgpu_group* g);
+int slgpu_group_size(const slgpu_group* g);
+slgpu_engine* slgpu_group_engine(slgpu_group* g, int i);
+slgpu_status slgpu_group_init_chains(slgpu_group* g);
+slgpu_status slgpu_group_step_rounds(slgpu_group* g, uint64_t n_rounds);
+slgpu_status slgpu_group_sync(slgpu_group* g);
+slgpu_status slgpu_group_run(slgpu_group* g);
+uint64_t slgpu_group_rounds_done(const slgpu_group* g);
+slgpu_status slgpu_group_rhat(slgpu_group* g, double* rhat);
+slgpu_status slgpu_group_summary(slgpu_group* g, char* json, size_t cap, size_t* needed);
+/* one checkpoint file per shard: <path>.stack<first global stack of the shard> */
+slgpu_status slgpu_group_save_state(slgpu_group* g, const char* path);
+slgpu_status slgpu_group_load_state(slgpu_group* g, const char* path);
+
 /* contract check: nll[point*J + job] = f(job, x[point*d ..]) through the plugin's functor (host buffers) */
 slgpu_status slgpu_eval_likelihood(slgpu_engine* e, const double* x, uint32_t n_points, double* nll);
 /* one State row as CSVChainArrayWriter prints it (db.cpp:18-25), no newline; returns the length */

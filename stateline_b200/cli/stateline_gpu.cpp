@@ -31,6 +31,7 @@ struct Options {
   int log_level = 0;                   // stateline.cpp:32
   int port = 5555;                     // stateline.cpp:33; accepted for compatibility, nothing listens
   std::string plugin, entry, payload, checkpoint, resume;
+  int gpus = 1;  // devices this one server process drives (0 = every visible device)
   bool help = false;
 };
 
@@ -44,6 +45,7 @@ void usage(const char* argv0) {
       "      --plugin FILE     Likelihood plugin .so (default: config \"gpu\".\"plugin\")\n"
       "      --entry SYMBOL    Plugin entry symbol (default: config \"gpu\".\"entry\", else slgpu_plugin_entry)\n"
       "      --payload FILE    Raw bytes handed to the plugin's functor (e.g. an array of doubles)\n"
+      "      --gpus N          Shard the stacks over N devices, gpu.device upwards (0 = all visible; default 1)\n"
       "      --checkpoint FILE Save the sampler state there on exit (also after Ctrl+C)\n"
       "      --resume FILE     Continue a run from a checkpoint instead of initialising the chains\n",
       argv0);
@@ -65,6 +67,7 @@ bool parse_args(int argc, char** argv, Options& o) {
     else if (a == "--plugin") { if (!value(o.plugin)) return false; }
     else if (a == "--entry") { if (!value(o.entry)) return false; }
     else if (a == "--payload") { if (!value(o.payload)) return false; }
+    else if (a == "--gpus") { if (!value(v)) return false; o.gpus = std::atoi(v.c_str()); }
     else if (a == "--checkpoint") { if (!value(o.checkpoint)) return false; }
     else if (a == "--resume") { if (!value(o.resume)) return false; }
     else return false;
@@ -105,17 +108,22 @@ std::string with_gpu_default(const std::string& text, const slgpu_json::Value& c
   return text.substr(0, at + 1) + item + (gpu->obj.empty() ? "" : ", ") + text.substr(at + 1);
 }
 
-int die(slgpu_engine* e, const char* what) {
+int die(slgpu_group* g, const char* what) {
   std::fprintf(stderr, "%s: %s\n", what, slgpu_last_error());  // LOG(FATAL) in the reference
-  if (e) slgpu_destroy(e);
+  if (g) slgpu_group_destroy(g);
   return 1;
 }
 
-void print_table(slgpu_engine* e) {
-  size_t need = 0;
-  if (slgpu_format_table(e, nullptr, 0, &need) != SLGPU_OK) return;
-  std::vector<char> buf(need);
-  if (slgpu_format_table(e, buf.data(), buf.size(), nullptr) == SLGPU_OK) std::fputs(buf.data(), stdout);
+// the reference prints one table for all chains (logging.cpp:52-87); a group prints one per device, chain ids local to it
+void print_table(slgpu_group* g) {
+  for (int i = 0; i < slgpu_group_size(g); ++i) {
+    slgpu_engine* e = slgpu_group_engine(g, i);
+    size_t need = 0;
+    if (slgpu_format_table(e, nullptr, 0, &need) != SLGPU_OK) return;
+    std::vector<char> buf(need);
+    if (slgpu_group_size(g) > 1) std::printf("\n[device shard %d]", i);
+    if (slgpu_format_table(e, buf.data(), buf.size(), nullptr) == SLGPU_OK) std::fputs(buf.data(), stdout);
+  }
   std::fflush(stdout);
 }
 
@@ -175,12 +183,13 @@ int main(int argc, char** argv) {
   std::signal(SIGINT, on_signal);
   std::signal(SIGTERM, on_signal);
 
-  slgpu_engine* e = nullptr;
-  if (slgpu_create(text.c_str(), opt.plugin.c_str(), opt.entry.empty() ? nullptr : opt.entry.c_str(),
-                   payload.empty() ? nullptr : payload.data(), payload.size(), &e) != SLGPU_OK)
-    return die(nullptr, "slgpu_create");
-  if (opt.resume.empty() ? slgpu_init_chains(e) != SLGPU_OK : slgpu_load_state(e, opt.resume.c_str()) != SLGPU_OK)
-    return die(e, opt.resume.empty() ? "slgpu_init_chains" : "slgpu_load_state");
+  // one process owns the whole run, as `stateline -c cfg` does (stateline.cpp:52-90): a group of --gpus devices
+  slgpu_group* g = nullptr;
+  if (slgpu_group_create(text.c_str(), opt.plugin.c_str(), opt.entry.empty() ? nullptr : opt.entry.c_str(),
+                         payload.empty() ? nullptr : payload.data(), payload.size(), nullptr, opt.gpus, &g) != SLGPU_OK)
+    return die(nullptr, "slgpu_group_create");
+  if (opt.resume.empty() ? slgpu_group_init_chains(g) != SLGPU_OK : slgpu_group_load_state(g, opt.resume.c_str()) != SLGPU_OK)
+    return die(g, opt.resume.empty() ? "slgpu_group_init_chains" : "slgpu_group_load_state");
 
   // stop rule, src/app/serverwrapper.cpp:100-107: cold-chain samples over all stacks >= nSamplesTotal
   const double n_stacks = cfg.find("nStacks")->num, n_total = cfg.find("nSamplesTotal")->num;
@@ -189,25 +198,33 @@ int main(int argc, char** argv) {
   using clock = std::chrono::steady_clock;
   auto last_print = clock::now();
   uint64_t chunk = 16;
-  while (!g_interrupted && slgpu_rounds_done(e) < total_rounds) {
-    const uint64_t n = std::min<uint64_t>(chunk, total_rounds - slgpu_rounds_done(e));
+  while (!g_interrupted && slgpu_group_rounds_done(g) < total_rounds) {
+    const uint64_t n = std::min<uint64_t>(chunk, total_rounds - slgpu_group_rounds_done(g));
     const auto t0 = clock::now();
-    if (slgpu_step_rounds(e, n) != SLGPU_OK) return die(e, "slgpu_step_rounds");
-    if (slgpu_sync(e) != SLGPU_OK) return die(e, "slgpu_sync");
+    if (slgpu_group_step_rounds(g, n) != SLGPU_OK) return die(g, "slgpu_group_step_rounds");
+    if (slgpu_group_sync(g) != SLGPU_OK) return die(g, "slgpu_group_sync");
     const double ms = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
     if (ms < 100.0 && chunk < (1u << 20)) chunk *= 2;  // keep Ctrl+C and the table responsive: ~0.1-0.2 s per chunk
     if (table && std::chrono::duration<double>(clock::now() - last_print).count() > log_sec) {
       last_print = clock::now();
-      print_table(e);
+      print_table(g);
     }
   }
-  if (slgpu_sync(e) != SLGPU_OK) return die(e, "slgpu_sync");  // Sampler::flush, sampler.cpp:216-235
-  if (table) print_table(e);
-  if (!opt.checkpoint.empty() && slgpu_save_state(e, opt.checkpoint.c_str()) != SLGPU_OK) return die(e, "slgpu_save_state");
+  if (slgpu_group_sync(g) != SLGPU_OK) return die(g, "slgpu_group_sync");  // Sampler::flush, sampler.cpp:216-235
+  if (table) print_table(g);
+  if (!opt.checkpoint.empty() && slgpu_group_save_state(g, opt.checkpoint.c_str()) != SLGPU_OK) return die(g, "slgpu_group_save_state");
   size_t need = 0;
-  slgpu_summary(e, nullptr, 0, &need);
-  std::vector<char> buf(need);
-  if (slgpu_summary(e, buf.data(), buf.size(), nullptr) == SLGPU_OK) std::printf("%s\n", buf.data());
-  slgpu_destroy(e);
+  std::vector<char> buf;
+  if (slgpu_group_size(g) == 1) {  // the single-device summary as before
+    slgpu_engine* e = slgpu_group_engine(g, 0);
+    slgpu_summary(e, nullptr, 0, &need);
+    buf.resize(need);
+    if (slgpu_summary(e, buf.data(), buf.size(), nullptr) == SLGPU_OK) std::printf("%s\n", buf.data());
+  } else {
+    slgpu_group_summary(g, nullptr, 0, &need);
+    buf.resize(need);
+    if (slgpu_group_summary(g, buf.data(), buf.size(), nullptr) == SLGPU_OK) std::printf("%s\n", buf.data());
+  }
+  slgpu_group_destroy(g);
   return g_interrupted ? 130 : 0;
 }

@@ -855,6 +855,9 @@ extern "C" {
 const char* slgpu_last_error(void) { return g_err.c_str(); }
 const char* slgpu_version(void) { return "slgpu 0.1 sm_100a"; }
 
+static slgpu_status create_from_settings(const Settings& cfg, const char* plugin_path, const char* plugin_entry, const void* payload,
+                                         size_t payload_bytes, slgpu_engine** out);
+
 slgpu_status slgpu_create(const char* config_json, const char* plugin_path, const char* plugin_entry, const void* payload,
                           size_t payload_bytes, slgpu_engine** out) {
   if (!config_json || !plugin_path || !out) return fail(SLGPU_E_ARG, "config_json, plugin_path and out must not be NULL");
@@ -865,6 +868,11 @@ slgpu_status slgpu_create(const char* config_json, const char* plugin_path, cons
   } catch (const ConfigError& ce) {
     return fail(SLGPU_E_CONFIG, ce.msg);
   }
+  return create_from_settings(cfg, plugin_path, plugin_entry, payload, payload_bytes, out);
+}
+
+static slgpu_status create_from_settings(const Settings& cfg, const char* plugin_path, const char* plugin_entry, const void* payload,
+                                         size_t payload_bytes, slgpu_engine** out) {
   // plugin
   void* dl = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
   if (!dl) return fail(SLGPU_E_PLUGIN, std::string("dlopen: ") + dlerror());
@@ -1845,6 +1853,190 @@ slgpu_status slgpu_measure_fp64_peak(int device, double* tflops) {
   cudaEventDestroy(b);
   cudaFree(sinkbuf);
   *tflops = best;
+  return SLGPU_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- several devices, one process
+// The reference is one `stateline -c cfg` process that owns the whole run (src/bin/stateline.cpp:52-90,
+// src/app/serverwrapper.cpp:44-138).  A group does that for several GPUs: the stacks are sharded contiguously, one
+// engine per device with its own tier models (the same thing as that many stateline servers), one host
+// thread per device for every call that queues work, and the end-of-run R-hat summed in this process.
+struct slgpu_group {
+  std::vector<slgpu_engine*> eng;
+  uint32_t n_stacks = 0, n_dims = 0;
+  uint64_t n_samples_total = 0;
+};
+
+namespace {
+template <class F>
+slgpu_status group_parallel(slgpu_group* g, F fn) {
+  const size_t n = g->eng.size();
+  std::vector<slgpu_status> st(n, SLGPU_OK);
+  std::vector<std::string> err(n);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < n; ++i)
+    th.emplace_back([&, i] {
+      st[i] = fn(g->eng[i]);
+      if (st[i] != SLGPU_OK) err[i] = g_err;  // the message lives in the worker thread
+    });
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < n; ++i)
+    if (st[i] != SLGPU_OK) return fail(st[i], "device " + std::to_string(g->eng[i]->cfg.device) + ": " + err[i]);
+  return SLGPU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+slgpu_status slgpu_group_create(const char* config_json, const char* plugin_path, const char* plugin_entry, const void* payload,
+                                size_t payload_bytes, const int* devices, int n_devices, slgpu_group** out) {
+  if (!config_json || !plugin_path || !out) return fail(SLGPU_E_ARG, "config_json, plugin_path and out must not be NULL");
+  *out = nullptr;
+  Settings cfg;
+  try {
+    cfg = parse_settings(config_json);
+  } catch (const ConfigError& ce) {
+    return fail(SLGPU_E_CONFIG, ce.msg);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SLGPU_E_CUDA, "no CUDA device: the engine has no CPU fallback");
+  std::vector<int> dev;
+  if (devices) {
+    if (n_devices <= 0) return fail(SLGPU_E_ARG, "n_devices must be positive when a device list is given");
+    dev.assign(devices, devices + n_devices);
+  } else {
+    const int n = n_devices > 0 ? n_devices : ndev;  // 0 = every device of the box
+    for (int i = 0; i < n; ++i) dev.push_back(cfg.device + i);
+  }
+  for (int dv : dev)
+    if (dv < 0 || dv >= ndev) return fail(SLGPU_E_CONFIG, "device " + std::to_string(dv) + " out of range (" + std::to_string(ndev) + " visible)");
+  const uint32_t G = (uint32_t)dev.size();
+  if (cfg.nStacks < G) return fail(SLGPU_E_CONFIG, "fewer stacks than devices");
+  slgpu_group* g = new slgpu_group();
+  g->n_stacks = cfg.nStacks;
+  g->n_dims = cfg.nDims;
+  g->n_samples_total = cfg.nSamplesTotal;
+  // the stop rule counts cold samples over ALL stacks (serverwrapper.cpp:100-107): every shard runs the same rounds
+  const uint64_t rounds = (cfg.nSamplesTotal + cfg.nStacks - 1) / cfg.nStacks;
+  const uint32_t base = cfg.nStacks / G, rem = cfg.nStacks % G;
+  uint32_t off = 0;
+  for (uint32_t i = 0; i < G; ++i) {
+    Settings c = cfg;
+    c.nStacks = base + (i < rem ? 1u : 0u);
+    c.device = dev[i];
+    c.stackOffset = cfg.stackOffset + off;
+    c.nSamplesTotal = rounds * c.nStacks;
+    off += c.nStacks;
+    slgpu_engine* e = nullptr;
+    const slgpu_status st = create_from_settings(c, plugin_path, plugin_entry, payload, payload_bytes, &e);
+    if (st != SLGPU_OK) {
+      const std::string keep = g_err;
+      slgpu_group_destroy(g);
+      return fail(st, keep);
+    }
+    g->eng.push_back(e);
+  }
+  *out = g;
+  return SLGPU_OK;
+}
+
+void slgpu_group_destroy(slgpu_group* g) {
+  if (!g) return;
+  for (slgpu_engine* e : g->eng) slgpu_destroy(e);
+  delete g;
+}
+
+int slgpu_group_size(const slgpu_group* g) { return g ? (int)g->eng.size() : 0; }
+slgpu_engine* slgpu_group_engine(slgpu_group* g, int i) { return (g && i >= 0 && i < (int)g->eng.size()) ? g->eng[i] : nullptr; }
+
+slgpu_status slgpu_group_init_chains(slgpu_group* g) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  return group_parallel(g, [](slgpu_engine* e) { return slgpu_init_chains(e); });
+}
+slgpu_status slgpu_group_step_rounds(slgpu_group* g, uint64_t n_rounds) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  return group_parallel(g, [n_rounds](slgpu_engine* e) { return slgpu_step_rounds(e, n_rounds); });
+}
+slgpu_status slgpu_group_sync(slgpu_group* g) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  return group_parallel(g, [](slgpu_engine* e) { return slgpu_sync(e); });
+}
+slgpu_status slgpu_group_run(slgpu_group* g) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  return group_parallel(g, [](slgpu_engine* e) { return slgpu_run(e); });
+}
+slgpu_status slgpu_group_save_state(slgpu_group* g, const char* path) {
+  if (!g || !path || !path[0]) return fail(SLGPU_E_ARG, "group and path must not be empty");
+  const std::string p = path;
+  return group_parallel(g, [&p](slgpu_engine* e) { return slgpu_save_state(e, (p + ".stack" + std::to_string(e->cfg.stackOffset)).c_str()); });
+}
+slgpu_status slgpu_group_load_state(slgpu_group* g, const char* path) {
+  if (!g || !path || !path[0]) return fail(SLGPU_E_ARG, "group and path must not be empty");
+  const std::string p = path;
+  return group_parallel(g, [&p](slgpu_engine* e) { return slgpu_load_state(e, (p + ".stack" + std::to_string(e->cfg.stackOffset)).c_str()); });
+}
+uint64_t slgpu_group_rounds_done(const slgpu_group* g) {
+  uint64_t r = ~0ull;
+  if (g)
+    for (const slgpu_engine* e : g->eng) r = std::min(r, e->rounds_done);
+  return (g && !g->eng.empty()) ? r : 0;
+}
+
+// EPSRDiagnostic::rHat (diagnostics.cpp:49-71) over the stacks of every device: the two-stage sums of slgpu_rhat_stage1/2
+slgpu_status slgpu_group_rhat(slgpu_group* g, double* rhat) {
+  if (!g || !rhat) return fail(SLGPU_E_ARG, "group and rhat must not be NULL");
+  const uint32_t d = g->n_dims;
+  std::vector<double> sum_m(d, 0.0), part(d), b(d, 0.0), w(d, 0.0), pb(d), pw(d), mean(d);
+  double m_total = 0.0, n_samples = 0.0;
+  for (slgpu_engine* e : g->eng) {
+    double ns = 0.0, nn = 0.0;
+    slgpu_status st = slgpu_rhat_stage1(e, part.data(), &ns, &nn);
+    if (st != SLGPU_OK) return st;
+    for (uint32_t i = 0; i < d; ++i) sum_m[i] += part[i];
+    m_total += ns;
+    n_samples = nn;
+  }
+  for (uint32_t i = 0; i < d; ++i) mean[i] = sum_m[i] / m_total;
+  for (slgpu_engine* e : g->eng) {
+    slgpu_status st = slgpu_rhat_stage2(e, mean.data(), pb.data(), pw.data());
+    if (st != SLGPU_OK) return st;
+    for (uint32_t i = 0; i < d; ++i) { b[i] += pb[i]; w[i] += pw[i]; }
+  }
+  slgpu_rhat_finish(b.data(), w.data(), m_total, n_samples, d, rhat);
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_group_summary(slgpu_group* g, char* json, size_t cap, size_t* needed) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  std::ostringstream o;
+  o.precision(10);
+  o << "{\"devices\":" << g->eng.size() << ",\"nStacks\":" << g->n_stacks << ",\"rhat\":[";
+  uint64_t rounds = slgpu_group_rounds_done(g);
+  if (rounds >= 2 && g->n_stacks >= 2) {
+    std::vector<double> r(g->n_dims);
+    slgpu_status st = slgpu_group_rhat(g, r.data());
+    if (st != SLGPU_OK) return st;
+    for (uint32_t i = 0; i < g->n_dims; ++i) o << (i ? "," : "") << r[i];
+  }
+  o << "],\"engines\":[";
+  for (size_t k = 0; k < g->eng.size(); ++k) {
+    size_t need = 0;
+    slgpu_status st = slgpu_summary(g->eng[k], nullptr, 0, &need);
+    if (st != SLGPU_OK) return st;
+    std::vector<char> buf(need);
+    if ((st = slgpu_summary(g->eng[k], buf.data(), buf.size(), nullptr)) != SLGPU_OK) return st;
+    o << (k ? "," : "") << "{\"device\":" << g->eng[k]->cfg.device << ",\"stackOffset\":" << g->eng[k]->cfg.stackOffset << ",\"summary\":" << buf.data() << "}";
+  }
+  o << "]}";
+  const std::string s = o.str();
+  if (needed) *needed = s.size() + 1;
+  if (json && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(json, s.data(), n);
+    json[n] = 0;
+  }
   return SLGPU_OK;
 }
 

@@ -31,6 +31,9 @@ SYMBOLS = [
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
     "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
     "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes",
+    "slgpu_group_create", "slgpu_group_destroy", "slgpu_group_size", "slgpu_group_engine", "slgpu_group_init_chains",
+    "slgpu_group_step_rounds", "slgpu_group_sync", "slgpu_group_run", "slgpu_group_rounds_done", "slgpu_group_rhat",
+    "slgpu_group_summary", "slgpu_group_save_state", "slgpu_group_load_state",
 ]
 
 
@@ -114,6 +117,22 @@ def lib():
     L.slgpu_release_segment.argtypes = [C.c_void_p]
     L.slgpu_d2h_bytes.argtypes = [C.c_void_p]
     L.slgpu_d2h_bytes.restype = C.c_uint64
+    L.slgpu_group_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int,
+                                     C.POINTER(C.c_void_p)]
+    L.slgpu_group_destroy.argtypes = [C.c_void_p]
+    L.slgpu_group_destroy.restype = None
+    L.slgpu_group_size.argtypes = [C.c_void_p]
+    L.slgpu_group_engine.argtypes = [C.c_void_p, C.c_int]
+    L.slgpu_group_engine.restype = C.c_void_p
+    for name in ("slgpu_group_init_chains", "slgpu_group_sync", "slgpu_group_run"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.slgpu_group_step_rounds.argtypes = [C.c_void_p, C.c_uint64]
+    L.slgpu_group_rounds_done.argtypes = [C.c_void_p]
+    L.slgpu_group_rounds_done.restype = C.c_uint64
+    L.slgpu_group_rhat.argtypes = [C.c_void_p, _dp]
+    L.slgpu_group_summary.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, _szp]
+    L.slgpu_group_save_state.argtypes = [C.c_void_p, C.c_char_p]
+    L.slgpu_group_load_state.argtypes = [C.c_void_p, C.c_char_p]
     _lib = L
     return L
 
@@ -397,3 +416,101 @@ def rhat_finish(sum_dm2, sum_s, n_stacks_total, n_samples):
     out = np.empty(sum_dm2.size)
     lib().slgpu_rhat_finish(_p(sum_dm2), _p(sum_s), float(n_stacks_total), float(n_samples), sum_dm2.size, _p(out))
     return out
+
+
+class _BorrowedEngine(Engine):
+    """An engine owned by an EngineGroup: same methods, the group destroys it."""
+
+    def __init__(self, handle, cfg, n_stacks):
+        L = lib()
+        self.h = C.c_void_p(handle)
+        self.cfg = cfg
+        self.S = n_stacks
+        self.T = cfg["nTemperatures"]
+        self.d = L.slgpu_n_dims(self.h)
+        self.C = L.slgpu_n_chains(self.h)
+        self.J = cfg["nJobTypes"]
+
+    def close(self):
+        self.h = None
+
+
+class EngineGroup:
+    """Several GPUs driven from one process through slgpu_group_* (include/slgpu.h): what one `stateline -c cfg` server
+    process is on the reference side (src/bin/stateline.cpp:52-90).  devices: None = every visible device from
+    gpu.device up, an int = that many, or an explicit list (a device may appear more than once)."""
+
+    def __init__(self, config, plugin=None, entry=None, payload=None, devices=None):
+        L = lib()
+        text = config if isinstance(config, str) else json.dumps(config)
+        if plugin is None or plugin in BUILTIN_ENTRIES:
+            entry = BUILTIN_ENTRIES[plugin or "demo_gauss"]
+            plugin = os.environ.get("SLGPU_TARGETS_SO") or _build.build_targets()
+        pl, n = None, 0
+        if payload is not None:
+            self._payload = np.ascontiguousarray(payload)
+            pl, n = self._payload.ctypes.data_as(C.c_void_p), self._payload.nbytes
+        if devices is None or isinstance(devices, int):
+            dev_ptr, n_dev = None, int(devices or 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            dev_ptr, n_dev = arr, len(devices)
+        h = C.c_void_p()
+        _check(L.slgpu_group_create(text.encode(), os.fspath(plugin).encode(), entry.encode() if entry else None, pl, n,
+                                    dev_ptr, n_dev, C.byref(h)))
+        self.h = h
+        self.cfg = json.loads(text)
+        self.d = len(self.cfg["min"])
+        size = L.slgpu_group_size(h)
+        S = self.cfg["nStacks"]
+        base, rem = divmod(S, size)
+        self.engines = [_BorrowedEngine(L.slgpu_group_engine(h, i), self.cfg, base + (1 if i < rem else 0)) for i in range(size)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            for e in self.engines:
+                e.close()
+            lib().slgpu_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def init_chains(self):
+        _check(lib().slgpu_group_init_chains(self.h))
+
+    def step_rounds(self, n):
+        _check(lib().slgpu_group_step_rounds(self.h, int(n)))
+
+    def sync(self):
+        _check(lib().slgpu_group_sync(self.h))
+
+    def run(self):
+        _check(lib().slgpu_group_run(self.h))
+
+    def save_state(self, path):
+        _check(lib().slgpu_group_save_state(self.h, os.fspath(path).encode()))
+
+    def load_state(self, path):
+        _check(lib().slgpu_group_load_state(self.h, os.fspath(path).encode()))
+
+    @property
+    def rounds_done(self):
+        return int(lib().slgpu_group_rounds_done(self.h))
+
+    def rhat(self):
+        out = np.empty(self.d)
+        _check(lib().slgpu_group_rhat(self.h, _p(out)))
+        return out
+
+    def summary(self):
+        need = C.c_size_t()
+        _check(lib().slgpu_group_summary(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().slgpu_group_summary(self.h, buf, need.value, None))
+        return json.loads(buf.value.decode())
