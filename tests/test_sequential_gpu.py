@@ -8,8 +8,9 @@ Two checks:
   * GPU == oracle (SLO_SCHED_SEQUENTIAL) bit for bit, native Philox draws and recorded draws;
   * the committed REFERENCE fixtures (tests/golden/ref_*.json: runs of the reference's own src/infer object code with
     the variates it drew, tests/golden/make_ref_golden.py) replayed on the GPU: identical accept / swap decisions and
-    logger counters; sigma / beta within 1e-12 relative; samples and energies within 1e-8 of max(|v|, 1) (the device
-    uses include/slgpu_math.h for exp / log, the reference glibc: at most 1 ulp apart per call).
+    logger counters; sigma / beta within 1e-12 relative; samples and energies of the cold chains within 1e-12 of
+    max(|v|, 1) (1e-10 on the double well), of all chains within 1e-9 (the device uses include/slgpu_math.h for exp / log,
+    the reference glibc: at most 1 ulp apart per call; tests/test_ref_pin.py states the per-tier measurements).
 """
 import json
 import os
@@ -21,7 +22,7 @@ from helpers import engine_for, oracle_for
 from oracle import oracle as O
 from stateline_b200 import configs
 from test_parity_gpu import _compare
-from test_ref_pin import FIXTURES, load_fixture
+from test_ref_pin import FIXTURES, REPLAY_HOT_BOUND, load_fixture, replay_cold_bound
 
 pytestmark = pytest.mark.gpu
 
@@ -80,7 +81,10 @@ def test_reference_fixture_replayed_on_gpu(path):
     for k in ("length", "accepts", "swaps", "swap_attempts"):  # every accept / swap decision of the whole run
         assert np.array_equal(gc[k].astype(np.float64), lg[k]), k
     scale = np.maximum(np.abs(ref[:, :d + 1]), 1.0)
-    assert np.max(np.abs(g[:, :d + 1] - ref[:, :d + 1]) / scale) < 1e-8
+    err = np.max(np.abs(g[:, :d + 1] - ref[:, :d + 1]) / scale, axis=1).reshape(cfg["S"], cfg["T"])
+    # per tier (tests/test_ref_pin.py: replay_cold_bound): the cold chains meet the north star's 1e-12 (1e-10 where the hot
+    # states reach the cold chain within the run), the chains at the sigma cap stay below 1e-9
+    assert err.max() < REPLAY_HOT_BOUND and err[:, 0].max() < replay_cold_bound(path)
     rs = np.array([float.fromhex(h) for h in fx["sigma"]])
     rb = np.array([float.fromhex(h) for h in fx["beta"]])
     assert np.max(np.abs(gs - rs) / rs) < 1e-12 and np.max(np.abs(gb - rb) / rb) < 1e-12
