@@ -134,6 +134,10 @@ uint64_t slgpu_d2h_bytes(const slgpu_engine* e);
 
 /* ---- device-side timing of what was queued between the two calls (CUDA events on the compute stream) ---- */
 slgpu_status slgpu_timer_start(slgpu_engine* e);
+/* the same without the event pair around every step-kernel launch (slgpu_timer_step_kernel reports 0 launches then): an
+ * event between two kernels keeps the second from starting early under programmatic dependent launch, so this is the
+ * timer that sees the step loop as it runs outside a measurement */
+slgpu_status slgpu_timer_start_coarse(slgpu_engine* e);
 slgpu_status slgpu_timer_stop(slgpu_engine* e, double* elapsed_ms); /* waits for the stop event */
 uint64_t slgpu_launch_count(const slgpu_engine* e);                 /* kernels launched so far */
 /* of the last timed region: summed device time of the step-kernel launches alone (their own event pairs) */

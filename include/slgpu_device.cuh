@@ -638,8 +638,19 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
       /* the opt-in is per device and context: set it on every launch (a process may drive several devices) */
       const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<D, NT>(1));
       if (attr != cudaSuccess) return (int)attr;
-      kern<<<grid_for(p, NT), NT, smem, (cudaStream_t)stream>>>(*p);
-      return (int)cudaGetLastError();
+      /* programmatic dependent launch: the kernel may start while the k_tier_adapt in front of it still runs and waits
+       * for it at cudaGridDependencySynchronize() (slgpu_step_fast.cuh); after any other kernel it starts as usual */
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(grid_for(p, NT));
+      lc.blockDim = dim3(NT);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute la[1];
+      la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      la[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = la;
+      lc.numAttrs = 1;
+      return (int)cudaLaunchKernelEx(&lc, kern, *p);
     }
 #endif
   }

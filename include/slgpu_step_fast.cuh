@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   const int tid = threadIdx.x;
 
   __shared__ double s_mn[D], s_mx[D], s_n0[D], s_rd[D];
-  __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
+  __shared__ double s_lad[SLGPU_MAX_TEMPS];
   /* dynamic shared memory (see fast_smem_bytes): three [D][NT] panels + the EPSR state of the block's stacks */
   extern __shared__ double s_dyn[];
   double* const s_jump = s_dyn;              /* staged accepted jumps, [i][slot] */
@@ -317,12 +317,10 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     s_n0[i] = p.n0_diag[i];
     s_rd[i] = 1.0 / (p.mx[i] - p.mn[i]);
   }
-  for (int i = tid; i < T; i += NT) {
-    s_w[3 * i + 0] = p.sig_w[3 * i + 0];
-    s_w[3 * i + 1] = p.sig_w[3 * i + 1];
-    s_w[3 * i + 2] = p.sig_w[3 * i + 2];
-    s_lad[i] = p.ladder[i];
-  }
+  /* s_w / s_lad (the tier models' outputs) and the pending regression statistics are loaded in round 0, behind
+   * cudaGridDependencySynchronize(): this kernel is launched with programmatic stream serialization, so everything up
+   * to there -- state loads, the first round's draws, proposal, likelihood and MH test -- may overlap the k_tier_adapt
+   * launch in front of it (which only produces those values) */
   if (tid < 2) s_nacc[tid] = 0;
   __syncthreads();
 
@@ -339,13 +337,13 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   }
   double Ps[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) Ps[k] = active ? p.p_sig[pidx(p, k, m.t, m.s)] : 0.0;
+  for (int k = 0; k < 9; ++k) Ps[k] = 0.0;
   double energy = p.energy[c], row_sigma = p.row_sigma[c], row_beta = p.row_beta[c];
   double sigma = p.sigma[c], beta = p.beta[c], nscale = p.nscale[c], sh_count = p.sh_count[c];
   int accepted = p.accepted[c], swap_type = p.swap_type[c];
   u32 lg_accepts = p.lg_accepts[c], lg_swaps = p.lg_swaps[c], lg_att = p.lg_swap_attempts[c];
   double lg_min_e = p.lg_min_energy[c];
-  const double w3[3] = {s_w[3 * m.t], s_w[3 * m.t + 1], s_w[3 * m.t + 2]};
+  double w3[3] = {0.0, 0.0, 0.0};
   const int W = (int)p.swap_interval;
   SLGPU_STAMP(1);
 
@@ -415,6 +413,17 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       }
       accepted = acc ? 1 : 0;
       swap_type = 0;
+    }
+    if (it == 0) { /* from here on the launch needs what k_tier_adapt wrote: wait for it (a no-op without PDL) */
+      cudaGridDependencySynchronize();
+      if (tid < T) s_lad[tid] = p.ladder[tid]; /* read after the next block barrier */
+      if (active) {
+        w3[0] = p.sig_w[3 * m.t]; w3[1] = p.sig_w[3 * m.t + 1]; w3[2] = p.sig_w[3 * m.t + 2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Ps[k] = p.p_sig[pidx(p, k, m.t, m.s)];
+      }
+    }
+    if (active) {
       /* sigma adaptation (sampler.cpp:160-162): statistics summed, model frozen for the launch */
       const double logtemper = -slm_log(row_beta);
       stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);

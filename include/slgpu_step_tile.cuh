@@ -95,7 +95,10 @@ struct TilePlan {
   static constexpr int oBnd = oScal + 192;  /* [4][D]    min, max, 1/(max-min), diag of the initial N */
   static constexpr int oPs = oBnd + 4 * D;  /* [9][32]   sigma regression statistics of the launch (warp 0) */
   static constexpr int oF = oPs + 9 * 32;   /* [J][32]   likelihood of every job type */
-  static size_t bytes(unsigned n_job_types) { return ((size_t)oF + (size_t)n_job_types * 32) * sizeof(double); }
+  /* + [2][D][stacks of the group] EPSR state behind the job panel */
+  static size_t bytes(unsigned n_job_types, unsigned n_temps) {
+    return ((size_t)oF + (size_t)n_job_types * 32 + (size_t)2 * D * (32u / n_temps)) * sizeof(double);
+  }
 };
 
 #ifdef SLGPU_STAMPS /* development: per-block clock stamps of round SLGPU_STAMPS into the round_flags buffer, 32 x i64 per block */
@@ -121,9 +124,10 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
   __shared__ int s_acc[32], s_src[32], s_fresh[32];
   __shared__ double s_w[SLGPU_MAX_TEMPS * 3], s_lad[SLGPU_MAX_TEMPS];
 
-  int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  asm volatile("" : "+r"(lane), "+r"(g)); /* keep them in registers: recomputing them from the thread id costs more */
-  const int tid = g * 32 + lane;
+  int lane, tidx;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane)); /* volatile: kept in a register, not re-read at every use */
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tidx));
+  const int g = tidx >> 5, tid = tidx;
   const int T = (int)p.n_temps, spw = 32 / T;
   const int sl = lane / T;
   const bool in_stack = sl < spw;
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
   const int oXl = Plan::oXp + lane * XS; /* this chain's proposal, contiguous */
   const int oFr = Plan::oXp + lane;      /* the same panel as [D][32] row sums at the end of the column sweep */
   const int oHl = Plan::oHead + lane;
+  const int oEp = Plan::oF + J * 32;     /* EPSRDiagnostic M and S of the group's stacks: [2][D][spw] */
 
   double* const gL = p.L + (size_t)blockIdx.x * NL * 32;
   if (tid == 0) mbar_init(&s_bar, 1);
@@ -163,6 +168,13 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
     s_w[3 * i + 2] = p.sig_w[3 * i + 2];
     s_lad[i] = p.ladder[i];
   }
+  for (int i = tid; i < D * spw; i += 32 * NW) { /* [j][stack of the group] */
+    const int j = i / spw, q = i - j * spw;
+    const u32 sq_ = blockIdx.x * (u32)spw + (u32)q;
+    const bool ok = sq_ < p.n_stacks;
+    s_dyn[oEp + i] = ok ? p.ep_m[(size_t)j * p.n_stacks + sq_] : 0.0;
+    s_dyn[oEp + D * spw + i] = ok ? p.ep_s[(size_t)j * p.n_stacks + sq_] : 0.0;
+  }
   double x[RM]; /* current sample, rows of this warp */
   int rowo[RM]; /* s_dyn offset of L(j, 0) of this lane's chain, rows of this warp */
 #pragma unroll
@@ -173,6 +185,8 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
   }
   /* per-chain scalars: warp 0 */
   double energy = 0.0, row_sigma = 1.0, row_beta = 1.0, sigma = 1.0, beta = 1.0, sh_count = 0.0, lg_min_e = 0.0;
+  double lt = 0.0, lrs = 0.0, lsig = 0.0; /* -log(row beta), log(row sigma), log(sigma): see the sigma sample below */
+  bool sig_fresh = false, rs_new = false, rb_new = false;
   int accepted = 0, swap_type = 0;
   u32 lg_accepts = 0, lg_swaps = 0, lg_att = 0;
   double w3[3] = {0.0, 0.0, 0.0};
@@ -182,6 +196,8 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
     accepted = p.accepted[c]; swap_type = p.swap_type[c];
     lg_accepts = p.lg_accepts[c]; lg_swaps = p.lg_swaps[c]; lg_att = p.lg_swap_attempts[c];
     lg_min_e = p.lg_min_energy[c];
+    lt = -slm_log(row_beta);
+    lrs = slm_log(row_sigma);
 #pragma unroll
     for (int k = 0; k < 9; ++k) s_dyn[Plan::oPs + k * 32 + lane] = active ? p.p_sig[pidx(p, k, t, s)] : 0.0;
     s_dyn[SIG + lane] = sigma;
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
     const bool swapRound = (T > 1) && ((r + 2) % (u64)W == 0);
     SLGPU_TSTAMP(0);
     /* ============ the round's draws: normals dealt to the warps by pair index (last warp first: warp 0 also draws
-     * the round's uniforms) ============ */
+     * the round's uniforms and prepares sqrt(count + 1) and friends for the chains that will accept) ============ */
 #pragma unroll 1
     for (int kp = NW - 1 - g; kp < NP; kp += NW) {
       double z0, z1 = 0.0;
@@ -235,12 +251,21 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
         philox_draw(p.seed, gchain, r, 1, 0, u_mh, ub);
         if (swapRound && active && t < T - 1) philox_draw(p.seed, gchain, r, 2, 0, u_sw, ub);
       }
+      /* ProposalShaper::update's scalars for count + 1 (adaptive.cpp:178-182): they do not depend on the decision, only
+       * whether they are used does; nobody reads them between here and the column sweep */
+      const double cnt1 = sh_count + 1.0;
+      const double sq = sqrt(cnt1);
+      s_dyn[SQ + lane] = sq;
+      s_dyn[RSQ + lane] = 1.0 / sq;
+      s_dyn[SCL + lane] = sqrt((cnt1 - 1.0) / cnt1);
     }
     __syncthreads();
     SLGPU_TSTAMP(1);
 
     /* ============ GaussianProposal::propose (sampler.cpp:79-93), rows of this warp: a_j = sum_{k<=j} fma(N_jk, z_k, .),
-     * k ascending, N = L * nscale + 1e-4 I (adaptive.cpp:200-204); the rows' chains run interleaved ============ */
+     * k ascending, N = L * nscale + 1e-4 I (adaptive.cpp:200-204).  The columns are walked in RM segments: in segment
+     * sgm the rows m >= sgm of this warp are still below their diagonal, so a segment has no per-element guard and its
+     * rows' chains run interleaved ============ */
     {
       const double nscale = s_dyn[NSC + lane];
       const double sig = s_dyn[SIG + lane];
@@ -248,13 +273,20 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
       double a[RM];
 #pragma unroll
       for (int m = 0; m < RM; ++m) a[m] = 0.0;
-      const int jlast = g + NW * (RM - 1) < D ? g + NW * (RM - 1) : g + NW * (RM - 2); /* my longest row */
-#pragma unroll 2
-      for (int k = 0; k < jlast; ++k) { /* strictly below the diagonal of my longest row */
-        const double zk = s_dyn[oZl + k * 32];
 #pragma unroll
-        for (int m = 0; m < RM; ++m)
-          if (k < g + NW * m && g + NW * m < D) a[m] = fma(s_dyn[rowo[m] + k * 32] * nscale, zk, a[m]);
+      for (int sgm = 0; sgm < RM; ++sgm) {
+        const int k0 = sgm == 0 ? 0 : g + NW * (sgm - 1);
+        const int k1 = (g + NW * sgm < D) ? g + NW * sgm : k0; /* rows beyond D do not exist */
+#pragma unroll 2
+        for (int k = k0; k < k1; ++k) {
+          const double zk = s_dyn[oZl + k * 32];
+          double lv[RM];
+#pragma unroll
+          for (int m = sgm; m < RM; ++m) lv[m] = (g + NW * m < D) ? s_dyn[rowo[m] + k * 32] : 0.0; /* below the diagonal of every existing row m >= sgm */
+#pragma unroll
+          for (int m = sgm; m < RM; ++m)
+            if (g + NW * m < D) a[m] = fma(lv[m] * nscale, zk, a[m]);
+        }
       }
 #pragma unroll
       for (int m = 0; m < RM; ++m) {
@@ -272,6 +304,7 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
     /* ============ likelihood: job types dealt to the warps (workerwrapper.hpp:21 contract, one chain per lane) ============ */
     if (active) {
       const double* xp = &s_dyn[oXl];
+#pragma unroll 2
       for (int q = g; q < J; q += NW) s_dyn[Plan::oF + q * 32 + lane] = lik((u32)q, xp, (u32)D);
     }
     __syncthreads();
@@ -290,13 +323,13 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
         }
         if (acc) {
           sh_count += 1.0;
-          const double sq = sqrt(sh_count);
-          s_dyn[SQ + lane] = sq;
-          s_dyn[RSQ + lane] = 1.0 / sq;
-          s_dyn[SCL + lane] = sqrt((sh_count - 1.0) / sh_count);
           energy = e_new;
-          row_sigma = sigma;
-          row_beta = beta;
+          row_sigma = sigma; /* the row takes the sigma and beta it was proposed with (chainarray.cpp:94-106) */
+          rs_new = true;
+          if (row_beta != beta) { /* only after the ladder moved: a swap round since the chain's last accept */
+            row_beta = beta;
+            rb_new = true;
+          }
         }
         accepted = acc ? 1 : 0;
         swap_type = 0;
@@ -337,7 +370,7 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
           V2n = Vn * Vn;
         }
       };
-      auto do_head = [&](double xk) -> double { /* publishes c, s, 1/c of column jn; returns r^2's root r */
+      auto do_head = [&](double xk) -> double { /* publishes c, s, 1/c of column jn; returns r */
         const double rr = sqrt(V2n + xk * xk);
         const double cc = div_by(rr, Vn, rVn);
         const double ss = div_by(xk, Vn, rVn);
@@ -349,6 +382,15 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
         if (accL) s_dyn[oLl + (jn * (jn + 1) / 2 + jn) * 32] = rr;
         return rr;
       };
+      auto sweep_row = [&](int m, int k, double cc, double ss, double rcc) { /* L(j_m, k) and x_j of row slot m */
+        const int o = rowo[m] + k * 32;
+        const double xj = xs[m];
+        double Ljk = s_dyn[o] * scale;
+        Ljk = div_by(Ljk + ss * xj, cc, rcc);
+        if (accL) s_dyn[o] = Ljk;
+        xs[m] = cc * xj - ss * Ljk;
+        fr[m] = fma(Ljk, Ljk, fr[m]);
+      };
       prep_head();
       if (g == 0) {
         const double rr = do_head(xs[0]);
@@ -358,12 +400,24 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
       }
       __syncthreads();
       if (g == 0) prep_head();
+      /* column k: its head is in shared memory.  The warp that owns row k+1 runs the serial chain first -- L(k+1,k), x_{k+1},
+       * head k+1 -- and hands it over at the barrier; its other rows of column k wait until after the barrier (they need
+       * nothing new, and nobody waits for them).  The other warps do their rows of column k while that head is computed. */
+      double pc = 0.0, ps = 0.0, prc = 0.0; /* column whose rows this warp still owes, after having been the owner */
+      int pk = -1;
 #pragma unroll 1
       for (int k = 0; k < D - 1; ++k) {
+        if (pk >= 0) { /* the rows I left behind as the owner of the previous head */
+#pragma unroll
+          for (int m = 0; m < RM; ++m) {
+            const int j = g + NW * m;
+            if (j > pk + 1 && j < D) sweep_row(m, pk, pc, ps, prc);
+          }
+          pk = -1;
+        }
         const int oh = oHl + (k & 1) * 96;
         const double cc = s_dyn[oh], ss = s_dyn[oh + 32], rcc = s_dyn[oh + 64];
-        const bool mine_next = (jn == k + 1); /* I own row k+1: the serial chain runs through me now */
-        if (mine_next) {
+        if (jn == k + 1) { /* I own row k+1: the serial chain runs through me now */
           double xj = xs[0];
           int ro = rowo[0];
 #pragma unroll
@@ -379,25 +433,25 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
 #pragma unroll
           for (int m = 0; m < RM; ++m)
             if (m == mn_) fr[m] = fma(rr, rr, fma(Ljk, Ljk, fr[m]));
-        }
-#pragma unroll
-        for (int m = 0; m < RM; ++m) { /* my other rows below row k+1 */
-          const int j = g + NW * m;
-          if (j > k + 1 && j < D) {
-            const int o = rowo[m] + k * 32;
-            const double xj = xs[m];
-            double Ljk = s_dyn[o] * scale;
-            Ljk = div_by(Ljk + ss * xj, cc, rcc);
-            if (accL) s_dyn[o] = Ljk;
-            xs[m] = cc * xj - ss * Ljk;
-            fr[m] = fma(Ljk, Ljk, fr[m]);
-          }
-        }
-        __syncthreads();
-        if (mine_next) { /* after the hand-over: the divisor of my next head */
+          pc = cc; ps = ss; prc = rcc; pk = k;
+          __syncthreads();
           jn += NW;
           mn_ += 1;
-          prep_head();
+          prep_head(); /* after the hand-over: the divisor of my next head */
+        } else {
+#pragma unroll
+          for (int m = 0; m < RM; ++m) {
+            const int j = g + NW * m;
+            if (j > k + 1 && j < D) sweep_row(m, k, cc, ss, rcc);
+          }
+          __syncthreads();
+        }
+      }
+      if (pk >= 0) {
+#pragma unroll
+        for (int m = 0; m < RM; ++m) {
+          const int j = g + NW * m;
+          if (j > pk + 1 && j < D) sweep_row(m, pk, pc, ps, prc);
         }
       }
       /* |L|_F: row sums to shared memory (the proposal panel is dead since the jumps were taken, and nobody writes it
@@ -476,12 +530,27 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
 
     /* ============ TableLogger counters (logging.cpp:35-48), cold row (db.cpp:18-25), EPSR (diagnostics.cpp:27-47) ============ */
     if (g == 0 && active) {
-      /* sigma adaptation sample (sampler.cpp:160-162) of this round's own decision and row: sigma and beta of a row
-       * do not move in a swap, so it can wait until here, off the column sweep's path (warp 0 owns head 0) */
-      const double logtemper = -slm_log(row_beta);
-      stats_accumulate<32>(&s_dyn[Plan::oPs + lane], -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
-      sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
-      s_dyn[SIG + lane] = sigma; /* read after the next round's first barrier */
+      /* sigma adaptation sample (sampler.cpp:160-162) of this round's own decision and row.  Sigma and beta of a row do
+       * not move in a swap, so it can wait until here, off the column sweep's path (warp 0 owns head 0).  It needs
+       * log(row sigma) and -log(row beta), and the next sigma is exp(predict(w, -log(row beta))) (adaptive.cpp:94-106,
+       * 134-139): the tier weights w are frozen for the launch and a row's sigma / beta only change on an accept, so the
+       * three are kept and recomputed only when their argument changes -- same functions, same arguments, same bits. */
+      if (rs_new) {
+        lrs = sig_fresh ? lsig : slm_log(row_sigma); /* sigma is still the one the row was proposed with */
+        rs_new = false;
+      }
+      if (rb_new) {
+        lt = -slm_log(row_beta);
+        sig_fresh = false;
+        rb_new = false;
+      }
+      stats_accumulate<32>(&s_dyn[Plan::oPs + lane], -8.0, 4.0, lrs, lt, acc);
+      if (!sig_fresh) { /* first round of the launch (new weights), or -log(row beta) just changed */
+        sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, lt));
+        lsig = slm_log(sigma);
+        sig_fresh = true;
+        s_dyn[SIG + lane] = sigma; /* read after the next round's first barrier */
+      }
       lg_min_e = smin(lg_min_e, mid_e);
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
@@ -508,12 +577,12 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
       for (int m = 0; m < RM; ++m) {
         const int j = g + NW * m;
         if (j < D) {
-          const size_t o = (size_t)j * p.n_stacks + s;
-          const double mo = p.ep_m[o];
+          const int o = oEp + j * spw + sl;
+          const double mo = s_dyn[o];
           const double xi = x[m];
           const double newM = mo + div_by(xi - mo, nn, rnn);
-          p.ep_s[o] = p.ep_s[o] + (xi - mo) * (xi - newM);
-          p.ep_m[o] = newM;
+          s_dyn[o + D * spw] = s_dyn[o + D * spw] + (xi - mo) * (xi - newM);
+          s_dyn[o] = newM;
           if (p.rows_out) p.rows_out[((size_t)it * p.n_stacks + s) * (D + SLGPU_ROW_EXTRA) + j] = xi;
         }
       }
@@ -539,8 +608,16 @@ __global__ void __launch_bounds__(32 * NW, SLGPU_TILE_MINBLOCKS) pt_step_tile_ke
     }
   }
   fence_async_smem();
-  __syncthreads(); /* every warp's last update of the tile and of nscale is in shared memory */
+  __syncthreads(); /* every warp's last update of the tile, of nscale and of the EPSR state is in shared memory */
   if (g == 0 && active) p.nscale[c] = s_dyn[NSC + lane];
+  for (int i = tid; i < D * spw; i += 32 * NW) {
+    const int j = i / spw, q = i - j * spw;
+    const u32 sq_ = blockIdx.x * (u32)spw + (u32)q;
+    if (sq_ < p.n_stacks) {
+      p.ep_m[(size_t)j * p.n_stacks + sq_] = s_dyn[oEp + i];
+      p.ep_s[(size_t)j * p.n_stacks + sq_] = s_dyn[oEp + D * spw + i];
+    }
+  }
   if (tid == 0 && dirty) bulk_store_and_wait(gL, &s_dyn[Plan::oL], NL * 32 * (unsigned)sizeof(double));
 }
 
@@ -548,7 +625,7 @@ template <class Lik, int D>
 inline int launch_step_tile(const slgpu_step_params* p, void* stream) {
   constexpr int NW = TileWarps<D>::value;
   auto kern = pt_step_tile_kernel<Lik, D, NW>;
-  const size_t smem = TilePlan<D>::bytes(p->n_job_types);
+  const size_t smem = TilePlan<D>::bytes(p->n_job_types, p->n_temps);
   /* the opt-in is per device: set it on every launch (a process may drive several devices) */
   const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return (int)attr;

@@ -158,6 +158,9 @@ __global__ void __launch_bounds__(256) k_tier_adapt(double* p_sig, double* p_bet
                                                     unsigned int* ticket, double* models, double* sig_w, double opt_swap,
                                                     double* ladder) {
   const uint32_t t = blockIdx.x, which = blockIdx.y, k = blockIdx.z, tid = threadIdx.x;
+  // the step kernel behind this launch may start now (programmatic dependent launch): it runs its first round up to the
+  // MH test on the chain state alone and waits for this grid before it reads the weights, the ladder or the statistics
+  cudaTriggerProgrammaticLaunchCompletion();
   double* P = (which ? p_beta : p_sig) + ((size_t)k * T + t) * S;
   __shared__ double a[256];
   __shared__ bool last;

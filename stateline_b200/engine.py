@@ -30,7 +30,7 @@ SYMBOLS = [
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
     "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
-    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes",
+    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes", "slgpu_timer_start_coarse",
     "slgpu_group_create", "slgpu_group_destroy", "slgpu_group_size", "slgpu_group_engine", "slgpu_group_init_chains",
     "slgpu_group_step_rounds", "slgpu_group_sync", "slgpu_group_run", "slgpu_group_rounds_done", "slgpu_group_rhat",
     "slgpu_group_summary", "slgpu_group_save_state", "slgpu_group_load_state",
@@ -85,6 +85,7 @@ def lib():
     L.slgpu_rows_emitted.argtypes = [C.c_void_p]
     L.slgpu_rows_emitted.restype = C.c_uint64
     L.slgpu_timer_start.argtypes = [C.c_void_p]
+    L.slgpu_timer_start_coarse.argtypes = [C.c_void_p]
     L.slgpu_timer_stop.argtypes = [C.c_void_p, _dp]
     L.slgpu_timer_step_kernel.argtypes = [C.c_void_p, _dp, _u64p]
     L.slgpu_launch_count.argtypes = [C.c_void_p]
@@ -277,8 +278,10 @@ class Engine:
     def launch_count(self):
         return lib().slgpu_launch_count(self.h)
 
-    def timer_start(self):
-        _check(lib().slgpu_timer_start(self.h))
+    def timer_start(self, per_launch=True):
+        """per_launch=False: no event pair around every step-kernel launch (they keep a kernel launched with programmatic
+        dependent launch from starting early): the step loop as it runs outside a measurement."""
+        _check((lib().slgpu_timer_start if per_launch else lib().slgpu_timer_start_coarse)(self.h))
 
     def timer_stop(self):
         ms = C.c_double()

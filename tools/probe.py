@@ -15,6 +15,7 @@ ap.add_argument("--rounds", type=int, default=500)
 ap.add_argument("--sink", default="device")
 ap.add_argument("--swap", type=int, default=0, help="override swapInterval")
 ap.add_argument("--mrl", type=int, default=64, help="gpu.maxRoundsPerLaunch")
+ap.add_argument("--coarse", action="store_true", help="no per-launch events (lets programmatic dependent launch overlap)")
 a = ap.parse_args()
 w = configs.workload(a.workload, S=a.stacks)
 if a.swap:
@@ -24,7 +25,7 @@ with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLa
     e.step_rounds(a.warm)
     e.sync()
     for rep in range(3):
-        e.timer_start()
+        e.timer_start(per_launch=not a.coarse)
         e.step_rounds(a.rounds)
         ms = e.timer_stop()
         kms, kn = e.timer_step_kernel()
