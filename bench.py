@@ -545,7 +545,7 @@ def run_group(args):
             g.sync()
             for e in g.engines:
                 while e.next_segment(block=True) is not None:
-                    e.release_segment()
+                    e.release_segment(keep_rows_state=False)
         b0 = sum(e.d2h_bytes for e in g.engines)
         seen = 0
         t0 = time.perf_counter()
@@ -557,7 +557,7 @@ def run_group(args):
                     if sg is None:
                         break
                     seen += int(np.count_nonzero(sg["flags"] & 1))
-                    e.release_segment()
+                    e.release_segment(keep_rows_state=False)
         g.sync()
         for e in g.engines:
             while True:
@@ -565,7 +565,7 @@ def run_group(args):
                 if sg is None:
                     break
                 seen += int(np.count_nonzero(sg["flags"] & 1))
-                e.release_segment()
+                e.release_segment(keep_rows_state=False)
         e2e_s = time.perf_counter() - t0
         d2h = (sum(e.d2h_bytes for e in g.engines) - b0) // K
     _emit(json.dumps({
@@ -719,7 +719,7 @@ def main():
             left -= n
             e.sync()
             while e.next_segment(block=True) is not None:
-                e.release_segment()
+                e.release_segment(keep_rows_state=False)
         barrier()
         b0 = e.d2h_bytes
         rows0 = e.rows_emitted
@@ -739,7 +739,7 @@ def main():
                 n_accept += int(np.count_nonzero(sg["flags"] & 1))
                 n_changed += sg["count"]
                 n_rows_seen += sg["flags"].size
-                e.release_segment()
+                e.release_segment(keep_rows_state=False)
                 in_flight -= 1
         t_enq = time.perf_counter()
         e.sync()                  # includes the D2H copies of the last segments
@@ -751,7 +751,7 @@ def main():
             n_changed += sg["count"]
             n_rows_seen += sg["flags"].size
             last_energy = float(sg["payload"][:, d].sum())  # the result of the last step, read on the host
-            e.release_segment()
+            e.release_segment(keep_rows_state=False)
         t1 = time.perf_counter()
         barrier()
         e2e_s = max_over_ranks(t1 - t0)
@@ -815,7 +815,8 @@ def main():
                 "note": "inputs are the resident chain state and on-device Philox draws: nothing to upload per step; the cold rows "
                         "reach pinned host memory as the delta stream (flag byte per row + the d+3 doubles of the rows whose cold "
                         "state changed; the host can rebuild every row exactly) inside the timed region; the host reads every flag "
-                        "byte of every segment and the energy column of the last segment",
+                        "byte of every segment and the energy column of the last segment, and hands the ring space back "
+                        "(slgpu_discard_segment: it does not rebuild rows)",
                 "rows": int(rows), "rows_changed": int(n_changed), "accepted_flags_seen": int(n_accept), "checksum": last_energy,
                 "host_loop_ms": {"enqueue_and_take": 1e3 * (t_enq - t0), "final_sync_and_take": 1e3 * (t1 - t_enq)},
                 "host_cpus_bound": (len(bound_cpus) if bound_cpus else None)},

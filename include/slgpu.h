@@ -129,6 +129,12 @@ typedef struct slgpu_segment {
 } slgpu_segment;
 slgpu_status slgpu_next_segment(slgpu_engine* e, int block, slgpu_segment* out);
 slgpu_status slgpu_release_segment(slgpu_engine* e);
+/* release without keeping the host's row-rebuilding state in step (slgpu_release_segment copies the changed rows for that:
+ * ~4 MB per segment at config #3).  For consumers that only ever take segments.  Afterwards slgpu_drain / slgpu_peek can
+ * rebuild rows again only from a key segment (SLGPU_E_STATE before that): slgpu_request_key_segment makes the next launch
+ * start one. */
+slgpu_status slgpu_discard_segment(slgpu_engine* e);
+slgpu_status slgpu_request_key_segment(slgpu_engine* e);
 /* bytes handed to the copy engine for the row sink so far (what `e2e.d2h_bytes_per_step` of bench.py counts) */
 uint64_t slgpu_d2h_bytes(const slgpu_engine* e);
 

@@ -197,7 +197,10 @@ struct slgpu_engine {
   std::deque<HostSeg> hsegs;           // enqueued, not yet released
   uint64_t rows_expanded = 0;          // rows materialised into `ring` so far (>= rows_consumed)
   std::vector<double> prev_row;        // [S][d+3] state of the expansion cursor
-  const double* prev_last_dev = nullptr;  // the previous launch's last round of full rows (device)
+  double* d_prev[2] = {nullptr, nullptr}; // the last round of full rows of the previous / of this launch (device, ping-pong)
+  int prev_cur = 0;                    // d_prev[prev_cur] holds the previous launch's last round
+  bool have_prev = false;
+  bool prev_valid = true;              // prev_row follows the stream (false after slgpu_discard_segment, until a key segment)
   bool force_key = true;               // the next segment must not lean on earlier rows
   double est_changed_per_round = -1.0; // payload rows per round of recent segments (sizes the copies)
   uint64_t d2h_bytes = 0;              // bytes handed to the copy engine so far
@@ -449,6 +452,11 @@ slgpu_status materialise(slgpu_engine* e) {
     }
     const HostSeg& hs = e->hsegs.front();
     const uint64_t end = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+    if (!e->prev_valid) {
+      if (((const uint32_t*)(e->cring + hs.off))[3] == 0)
+        return fail(SLGPU_E_STATE, "rows cannot be rebuilt from here: segments were discarded (slgpu_discard_segment) and this one is not a key segment");
+      e->prev_valid = true;
+    }
     if (e->cfg.overwrite && end > e->rows_consumed + e->ring_rows) e->rows_consumed = end - e->ring_rows;
     apply_segment(e, hs, e->ring);
     e->rows_expanded = end;
@@ -685,10 +693,13 @@ slgpu_status enqueue_compact(slgpu_engine* e, const double* rows_dev, uint32_t n
     }
   }
   const SegLayout L = seg_layout(n_rounds, S);
-  const bool key = e->force_key || e->cfg.overwrite || !e->prev_last_dev;
+  const bool key = e->force_key || e->cfg.overwrite || !e->have_prev;
   CU_TRY(cudaMemsetAsync(cb.dev, 0, 16, e->compute));
   slgpu_rows::k_compact_rows<<<dim3(L.n_chunks, n_rounds), slgpu_rows::kChunk, 0, e->compute>>>(
-      rows_dev, e->prev_last_dev, S, e->row_w, n_rounds, key ? 1 : 0, cb.dev, L.n_chunks, (uint32_t)L.off_flags, (uint32_t)L.off_payload);
+      rows_dev, e->d_prev[e->prev_cur], e->d_prev[e->prev_cur ^ 1], S, e->row_w, n_rounds, key ? 1 : 0, cb.dev, L.n_chunks,
+      (uint32_t)L.off_flags, (uint32_t)L.off_payload);
+  e->prev_cur ^= 1;
+  e->have_prev = true;
   CU_TRY(cudaGetLastError());
   e->launches++;
   CU_TRY(cudaEventRecord(cb.written, e->compute));
@@ -718,7 +729,6 @@ slgpu_status enqueue_compact(slgpu_engine* e, const double* rows_dev, uint32_t n
   CU_TRY(cudaEventRecord(hs.ev, e->drain));
   e->hsegs.push_back(hs);
   e->rows_enq += (uint64_t)n_rounds * S;
-  e->prev_last_dev = rows_dev + (size_t)(n_rounds - 1) * S * e->row_w;
   e->force_key = false;
   return SLGPU_OK;
 }
@@ -1008,7 +1018,9 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
     }
     if (cfg.sink != SINK_NONE) {
       const size_t seg_doubles = (size_t)e->seg_rounds * S * e->row_w;
-      const int nseg = (cfg.sink == SINK_DEVICE) ? 1 : kSegments;  // wire "delta" compares a launch with the previous one: distinct buffers
+      // full rows leave the device only on wire "full" (three buffers in flight); on the delta wire k_compact_rows consumes a
+      // launch's rows on the compute stream before the next launch writes them: one buffer, re-used, stays in L2
+      const int nseg = (cfg.sink == SINK_DEVICE || cfg.wire == WIRE_DELTA) ? 1 : kSegments;
       for (int i = 0; i < kSegments; ++i) {
         if (i < nseg) {
           TRY_ST(dev_alloc(e, &e->seg[i].dev, seg_doubles));
@@ -1029,6 +1041,8 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
         const size_t maxseg = seg_layout(e->seg_rounds, S).bytes(e->seg_rounds * S, d) + 256;
         e->cring_bytes = e->ring_rows * e->row_w * sizeof(double) + (size_t)(rr + 4) * 512 + 2 * maxseg;
         CU_TRY(cudaHostAlloc((void**)&e->cring, e->cring_bytes, cudaHostAllocDefault));
+        TRY_ST(dev_alloc(e, &e->d_prev[0], (size_t)S * e->row_w));
+        TRY_ST(dev_alloc(e, &e->d_prev[1], (size_t)S * e->row_w));
         for (int i = 0; i < kCompactBufs; ++i) {
           TRY_ST(dev_alloc(e, &e->cbuf[i].dev, maxseg));
           CU_TRY(cudaEventCreateWithFlags(&e->cbuf[i].written, cudaEventDisableTiming));
@@ -1170,7 +1184,6 @@ slgpu_status slgpu_init_chains(slgpu_engine* e) {
     if (to_host) {
       if (delta_wire(e)) {
         e->force_key = true;  // the initial rows are everybody's first row
-        e->prev_last_dev = nullptr;
         if ((st = enqueue_compact(e, sg.dev, 1)) != SLGPU_OK) return st;
       } else {
         CU_TRY(cudaEventRecord(sg.written, e->compute));
@@ -1336,10 +1349,28 @@ slgpu_status slgpu_release_segment(slgpu_engine* e) {
   if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
   if (e->hsegs.empty() || !e->hsegs.front().landed) return fail(SLGPU_E_STATE, "no landed segment to release");
   const HostSeg& hs = e->hsegs.front();
-  apply_segment(e, hs, nullptr);  // a later slgpu_drain starts from the right rows
+  if (!e->prev_valid && ((const uint32_t*)(e->cring + hs.off))[3] != 0) e->prev_valid = true;
+  if (e->prev_valid) apply_segment(e, hs, nullptr);  // a later slgpu_drain starts from the right rows
   e->rows_consumed = e->rows_expanded = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
   e->rows_landed = std::max(e->rows_landed, e->rows_consumed);
   release_front_segment(e);
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_discard_segment(slgpu_engine* e) {
+  if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
+  if (e->hsegs.empty() || !e->hsegs.front().landed) return fail(SLGPU_E_STATE, "no landed segment to discard");
+  const HostSeg& hs = e->hsegs.front();
+  e->rows_consumed = e->rows_expanded = hs.row_begin + (uint64_t)hs.n_rounds * e->cfg.nStacks;
+  e->rows_landed = std::max(e->rows_landed, e->rows_consumed);
+  e->prev_valid = false;  // the expansion state no longer follows the stream: rows can be rebuilt again from a key segment
+  release_front_segment(e);
+  return SLGPU_OK;
+}
+
+slgpu_status slgpu_request_key_segment(slgpu_engine* e) {
+  if (!e) return fail(SLGPU_E_ARG, "engine is NULL");
+  e->force_key = true;
   return SLGPU_OK;
 }
 
@@ -1832,7 +1863,6 @@ slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
   e->rounds_done = h.rounds_done;
   e->initialised = true;
   e->force_key = true;  // the resumed stream starts with a key segment: the host has no earlier row to lean on
-  e->prev_last_dev = nullptr;
   return SLGPU_OK;
 }
 

@@ -20,32 +20,41 @@ namespace slgpu_rows {
 constexpr int kChunk = 256;  // stacks per block = per base entry
 
 // grid (n_chunks, n_rounds), 256 threads.  rows: this launch's full rows [n_rounds][S][w] (w = d + 5);
-// prev_last: the previous launch's last round [S][w] (ignored when key != 0: every row of round 0 is then "changed").
+// prev_in: the previous launch's last round [S][w] (ignored when key != 0: every row of round 0 is then "changed");
+// prev_out: receives this launch's last round (a different buffer from prev_in: the blocks of round 0 still read that).
 // out: the compact segment; its count word (out + 8) must be zero on entry.
-__global__ void __launch_bounds__(kChunk) k_compact_rows(const double* __restrict__ rows, const double* __restrict__ prev_last,
-                                                         uint32_t S, uint32_t w, uint32_t n_rounds, int key, unsigned char* out,
-                                                         uint32_t n_chunks, uint32_t off_flags, uint32_t off_payload) {
+__global__ void __launch_bounds__(kChunk) k_compact_rows(const double* __restrict__ rows, const double* __restrict__ prev_in,
+                                                         double* __restrict__ prev_out, uint32_t S, uint32_t w, uint32_t n_rounds,
+                                                         int key, unsigned char* out, uint32_t n_chunks, uint32_t off_flags,
+                                                         uint32_t off_payload) {
   const uint32_t chunk = blockIdx.x, round = blockIdx.y, tid = threadIdx.x;
   const uint32_t s0 = chunk * kChunk;
   const uint32_t nrow = (S - s0 < (uint32_t)kChunk) ? S - s0 : (uint32_t)kChunk;
   const uint32_t wp = w - 2;  // payload doubles per row
   const double* cur = rows + ((size_t)round * S + s0) * w;
-  const double* prev = round ? cur - (size_t)S * w : prev_last + (size_t)s0 * w;
+  const double* prev = round ? cur - (size_t)S * w : prev_in + (size_t)s0 * w;
   const bool all = (round == 0 && key != 0);
+  const bool last_round = (round + 1 == n_rounds);
   __shared__ int s_ch[kChunk];
   __shared__ uint32_t s_slot[kChunk];
   __shared__ uint32_t s_warp[kChunk / 32];
   __shared__ uint32_t s_base;
   s_ch[tid] = (all && tid < nrow) ? 1 : 0;
   __syncthreads();
-  if (!all) {
-    const uint32_t n = nrow * w;
+  const uint32_t n = nrow * w;
+  const uint32_t dr = (uint32_t)kChunk / w, dc = (uint32_t)kChunk - dr * w;  // a stride of 256 doubles in (row, column) steps
+  {
+    uint32_t r = tid / w, c = tid - r * w;
     for (uint32_t i = tid; i < n; i += kChunk) {  // consecutive threads, consecutive doubles
-      const uint32_t r = i / w, c = i - r * w;
-      if (c < wp && __double_as_longlong(cur[i]) != __double_as_longlong(prev[i])) s_ch[r] = 1;  // same value from every writer
+      const double v = cur[i];
+      if (!all && c < wp && __double_as_longlong(v) != __double_as_longlong(prev[i])) s_ch[r] = 1;  // same value from every writer
+      if (last_round) prev_out[(size_t)s0 * w + i] = v;
+      r += dr;
+      c += dc;
+      if (c >= w) { c -= w; r += 1; }
     }
-    __syncthreads();
   }
+  __syncthreads();
   // exclusive scan of the changed flags over the chunk: slots follow the stack order
   const int ch = s_ch[tid];
   const uint32_t lane = tid & 31, wid = tid >> 5;
@@ -77,10 +86,12 @@ __global__ void __launch_bounds__(kChunk) k_compact_rows(const double* __restric
   __syncthreads();
   if (total == 0) return;
   double* pay = (double*)(out + off_payload) + (size_t)s_base * wp;
-  const uint32_t n = nrow * w;
+  uint32_t r = tid / w, c = tid - r * w;
   for (uint32_t i = tid; i < n; i += kChunk) {
-    const uint32_t r = i / w, c = i - r * w;
     if (c < wp && s_ch[r]) pay[(size_t)s_slot[r] * wp + c] = cur[i];
+    r += dr;
+    c += dc;
+    if (c >= w) { c -= w; r += 1; }
   }
 }
 

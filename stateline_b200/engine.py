@@ -30,7 +30,7 @@ SYMBOLS = [
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
     "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
-    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes", "slgpu_timer_start_coarse",
+    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes", "slgpu_timer_start_coarse", "slgpu_discard_segment", "slgpu_request_key_segment",
     "slgpu_group_create", "slgpu_group_destroy", "slgpu_group_size", "slgpu_group_engine", "slgpu_group_init_chains",
     "slgpu_group_step_rounds", "slgpu_group_sync", "slgpu_group_run", "slgpu_group_rounds_done", "slgpu_group_rhat",
     "slgpu_group_summary", "slgpu_group_save_state", "slgpu_group_load_state",
@@ -116,6 +116,8 @@ def lib():
     L.slgpu_load_state.argtypes = [C.c_void_p, C.c_char_p]
     L.slgpu_next_segment.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Segment)]
     L.slgpu_release_segment.argtypes = [C.c_void_p]
+    L.slgpu_discard_segment.argtypes = [C.c_void_p]
+    L.slgpu_request_key_segment.argtypes = [C.c_void_p]
     L.slgpu_d2h_bytes.argtypes = [C.c_void_p]
     L.slgpu_d2h_bytes.restype = C.c_uint64
     L.slgpu_group_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int,
@@ -337,8 +339,15 @@ class Engine:
                     flags=as_array(sg.flags, shape=(sg.n_rounds, sg.n_stacks)),
                     payload=as_array(sg.payload, shape=(max(sg.count, 1), sg.payload_doubles))[:sg.count])
 
-    def release_segment(self):
-        _check(lib().slgpu_release_segment(self.h))
+    def release_segment(self, keep_rows_state=True):
+        """keep_rows_state=False (slgpu_discard_segment): the host stops tracking the rows behind the stream (cheaper; a later
+        drain() needs a key segment first: request_key_segment())."""
+        _check((lib().slgpu_release_segment if keep_rows_state else lib().slgpu_discard_segment)(self.h))
+
+    def request_key_segment(self):
+        """The next launch starts a key segment (every row of its first round in the payload): after discarded segments,
+        drain() / peek() can rebuild rows again from there."""
+        _check(lib().slgpu_request_key_segment(self.h))
 
     @property
     def d2h_bytes(self):

@@ -138,3 +138,38 @@ def test_overwrite_and_resume_start_with_key_segments(tmp_path):
         assert sg["key"]
         rows = eng.drain().reshape(65, S, d + 5)
     assert np.array_equal(rows, want[-65:])
+
+
+def test_discarded_segments_and_the_next_key_segment():
+    """slgpu_discard_segment: the cheap release for consumers that only take segments.  The host's row state is then
+    stale: drain() works again from a key segment (slgpu_request_key_segment), a non-key segment before that is refused."""
+    from stateline_b200 import SlgpuError
+    S, d = 48, 20
+    w = configs.workload("config3", S=S)
+    want = _oracle_rows(w, 13, 60)
+    with engine_for(w, seed=13) as eng:
+        eng.init_chains()
+        eng.step_rounds(30)
+        eng.sync()
+        n = 0
+        while True:
+            sg = eng.next_segment(block=True)
+            if sg is None:
+                break
+            n += sg["n_rounds"]
+            eng.release_segment(keep_rows_state=False)
+        assert n == 31
+        eng.request_key_segment()
+        eng.step_rounds(30)
+        sg = eng.next_segment(block=True)
+        assert sg["key"]
+        rows = eng.drain().reshape(30, S, d + 5)
+        assert np.array_equal(rows, want[31:])
+    with engine_for(w, seed=13) as eng:
+        eng.init_chains()
+        eng.step_rounds(30)  # several non-key segments are queued behind the initial one
+        eng.sync()
+        eng.next_segment(block=True)
+        eng.release_segment(keep_rows_state=False)
+        with pytest.raises(SlgpuError):
+            eng.drain()
