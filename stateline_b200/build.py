@@ -13,6 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 
 ENGINE_SO = os.path.join(PKG, "libslgpu.so")
 TARGETS_SO = os.path.join(PKG, "libslgpu_targets.so")
+TARGETS_TILE_SO = os.path.join(PKG, "libslgpu_targets_tile.so")  # the same targets on the opt-in tile kernel
 CLI_EXE = os.path.join(PKG, "stateline-gpu")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -91,6 +92,12 @@ def build_targets(force=False, verbose=False):
     return build_plugin(os.path.join(PKG, "plugins", "builtin_targets.cu"), TARGETS_SO, force, verbose)
 
 
+def build_targets_tile(force=False, verbose=False):
+    """The built-in targets with -DSLGPU_TILE_KERNEL: the step kernel that keeps a stack group's factors in shared memory
+    for the launch (include/slgpu_step_tile.cuh).  Opt-in (slower than the default); built so that its tests travel."""
+    return build_plugin(os.path.join(PKG, "plugins", "builtin_targets.cu"), TARGETS_TILE_SO, force, verbose, extra=("-DSLGPU_TILE_KERNEL",))
+
+
 def build_cli(force=False, verbose=False, out=CLI_EXE):
     """stateline-gpu: the `stateline -c config.json` server binary for the GPU path (plain C++ over the C-ABI)."""
     build_engine(force, verbose)
@@ -106,6 +113,7 @@ def build_cli(force=False, verbose=False, out=CLI_EXE):
 
 
 def build_all(force=False, verbose=False):
+    build_targets_tile(force, verbose)
     return build_engine(force, verbose), build_targets(force, verbose), build_cli(force, verbose)
 
 

@@ -288,3 +288,36 @@ def test_tier_reduce_across_many_stacks(S):
         eng.step_rounds(16)
         _compare(eng, orc, w, "tier reduce S=%d" % S)
         _compare_all_rows(eng, orc, w, 16)
+
+
+@pytest.fixture(scope="module")
+def tile_plugin():
+    """The built-in targets compiled with -DSLGPU_TILE_KERNEL: the opt-in step kernel that keeps a stack group's factors in
+    shared memory for the launch (include/slgpu_step_tile.cuh); stateline_b200/build.py builds it in-tree."""
+    from stateline_b200 import build
+    return build.build_targets_tile()
+
+
+@pytest.mark.parametrize("name,S,rounds,kw", [("config1", 2, 61, {}), ("config2", 37, 45, {}), ("config3", 520, 31, {}),
+                                             ("config3", 8192, 21, {}), ("config3", 5, 33, dict(rng="replay"))])
+def test_tile_kernel_bit_exact(tile_plugin, name, S, rounds, kw, monkeypatch):
+    """Same bits from the opt-in tile kernel: README demo (T = 5: idle lanes), double well (d = 2: two warps per group),
+    config #3 at a ragged size and at the bench size, and replay mode."""
+    monkeypatch.setenv("SLGPU_TARGETS_SO", tile_plugin)
+    w = configs.workload(name, S=S)
+    if kw.get("rng") == "replay":
+        z, u_mh, u_swap, x_init = make_replay(w["S"], w["T"], w["d"], rounds, seed=4)
+        orc = oracle_for(w, rng_mode=O.RNG_REPLAY)
+        orc.set_replay(z, u_mh, u_swap, x_init)
+    else:
+        orc = oracle_for(w, seed=9)
+    orc.init_chains()
+    orc.run_rounds(rounds)
+    with engine_for(w, seed=9, hostRingRounds=rounds + 2, **kw) as eng:
+        if kw.get("rng") == "replay":
+            eng.set_replay(z, u_mh, u_swap, x_init)
+        eng.init_chains()
+        for chunk in (1, 9, rounds - 10):
+            eng.step_rounds(chunk)
+        _compare(eng, orc, w, "tile kernel %s S=%d" % (name, S))
+        _compare_all_rows(eng, orc, w, rounds)
