@@ -97,6 +97,9 @@ slgpu_status slgpu_init_chains(slgpu_engine* e);
 slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds);
 /* wait for everything queued so far; reports asynchronous CUDA errors */
 slgpu_status slgpu_sync(slgpu_engine* e);
+/* wait for everything queued so far WITHOUT finalising the sink (the csv sink keeps its text buffers for the next 64 MiB /
+ * end-of-run flush instead of re-opening every <stack>.csv): what a host loop calls between chunks */
+slgpu_status slgpu_wait(slgpu_engine* e);
 /* the reference's whole run: init (if needed), ceil(nSamplesTotal / nStacks) rounds, flush the sink */
 slgpu_status slgpu_run(slgpu_engine* e);
 uint64_t slgpu_rounds_done(const slgpu_engine* e);
@@ -217,6 +220,7 @@ slgpu_engine* slgpu_group_engine(slgpu_group* g, int i);
 slgpu_status slgpu_group_init_chains(slgpu_group* g);
 slgpu_status slgpu_group_step_rounds(slgpu_group* g, uint64_t n_rounds);
 slgpu_status slgpu_group_sync(slgpu_group* g);
+slgpu_status slgpu_group_wait(slgpu_group* g);
 slgpu_status slgpu_group_run(slgpu_group* g);
 uint64_t slgpu_group_rounds_done(const slgpu_group* g);
 slgpu_status slgpu_group_rhat(slgpu_group* g, double* rhat);

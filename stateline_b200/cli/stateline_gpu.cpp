@@ -202,7 +202,7 @@ int main(int argc, char** argv) {
     const uint64_t n = std::min<uint64_t>(chunk, total_rounds - slgpu_group_rounds_done(g));
     const auto t0 = clock::now();
     if (slgpu_group_step_rounds(g, n) != SLGPU_OK) return die(g, "slgpu_group_step_rounds");
-    if (slgpu_group_sync(g) != SLGPU_OK) return die(g, "slgpu_group_sync");
+    if (slgpu_group_wait(g) != SLGPU_OK) return die(g, "slgpu_group_wait");  // no sink flush per chunk: that is for the end
     const double ms = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
     if (ms < 100.0 && chunk < (1u << 20)) chunk *= 2;  // keep Ctrl+C and the table responsive: ~0.1-0.2 s per chunk
     if (table && std::chrono::duration<double>(clock::now() - last_print).count() > log_sec) {

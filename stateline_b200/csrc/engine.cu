@@ -1236,6 +1236,17 @@ slgpu_status slgpu_sync(slgpu_engine* e) {
   return SLGPU_OK;
 }
 
+/* wait for the queued rounds without finalising the sink: the csv sink formats what has landed but leaves its buffers
+ * to the 64 MiB / end-of-run flush (slgpu_sync re-opens and closes every <stack>.csv) */
+slgpu_status slgpu_wait(slgpu_engine* e) {
+  slgpu_status st = check_ready(e, false);
+  if (st != SLGPU_OK) return st;
+  if ((st = sync_all(e)) != SLGPU_OK) return st;
+  if (e->cfg.sink == SINK_CSV && e->initialised) return csv_pump(e, true, false);
+  if (e->cfg.sink == SINK_BIN && e->initialised) return bin_pump(e, true, false);
+  return SLGPU_OK;
+}
+
 slgpu_status slgpu_run(slgpu_engine* e) {
   slgpu_status st = check_ready(e, false);
   if (st != SLGPU_OK) return st;
@@ -2008,6 +2019,10 @@ slgpu_status slgpu_group_step_rounds(slgpu_group* g, uint64_t n_rounds) {
 slgpu_status slgpu_group_sync(slgpu_group* g) {
   if (!g) return fail(SLGPU_E_ARG, "group is NULL");
   return group_parallel(g, [](slgpu_engine* e) { return slgpu_sync(e); });
+}
+slgpu_status slgpu_group_wait(slgpu_group* g) {
+  if (!g) return fail(SLGPU_E_ARG, "group is NULL");
+  return group_parallel(g, [](slgpu_engine* e) { return slgpu_wait(e); });
 }
 slgpu_status slgpu_group_run(slgpu_group* g) {
   if (!g) return fail(SLGPU_E_ARG, "group is NULL");

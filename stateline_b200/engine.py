@@ -30,7 +30,7 @@ SYMBOLS = [
     "slgpu_get_counters", "slgpu_rhat", "slgpu_rhat_stage1", "slgpu_rhat_stage2", "slgpu_rhat_finish",
     "slgpu_summary", "slgpu_eval_likelihood", "slgpu_format_row", "slgpu_measure_fp64_peak",
     "slgpu_save_state", "slgpu_load_state", "slgpu_get_logger", "slgpu_format_table",
-    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes", "slgpu_timer_start_coarse", "slgpu_discard_segment", "slgpu_request_key_segment",
+    "slgpu_next_segment", "slgpu_release_segment", "slgpu_d2h_bytes", "slgpu_timer_start_coarse", "slgpu_discard_segment", "slgpu_request_key_segment", "slgpu_wait", "slgpu_group_wait",
     "slgpu_group_create", "slgpu_group_destroy", "slgpu_group_size", "slgpu_group_engine", "slgpu_group_init_chains",
     "slgpu_group_step_rounds", "slgpu_group_sync", "slgpu_group_run", "slgpu_group_rounds_done", "slgpu_group_rhat",
     "slgpu_group_summary", "slgpu_group_save_state", "slgpu_group_load_state",
@@ -76,6 +76,8 @@ def lib():
     L.slgpu_init_chains.argtypes = [C.c_void_p]
     L.slgpu_step_rounds.argtypes = [C.c_void_p, C.c_uint64]
     L.slgpu_sync.argtypes = [C.c_void_p]
+    L.slgpu_wait.argtypes = [C.c_void_p]
+    L.slgpu_group_wait.argtypes = [C.c_void_p]
     L.slgpu_run.argtypes = [C.c_void_p]
     L.slgpu_rounds_done.argtypes = [C.c_void_p]
     L.slgpu_rounds_done.restype = C.c_uint64
