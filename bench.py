@@ -842,6 +842,23 @@ def main():
                 out["configs"][name] = side_config(name, Sside, local_rank, peaks, fp64_peak)
             except Exception as ex:
                 sys.stderr.write("side config %s failed (%r)\n" % (name, ex))
+    if not args.no_side and world == 1:
+        # the opt-in non-reference shaper (north star's "Welford + periodic re-Cholesky"): same workload, same timer, for context
+        try:
+            cfg_w = configs.engine_config(w, sink="device", device=local_rank, seed=1234, shaper="welford")
+            with Engine(cfg_w, plugin=w["plugin"], payload=w["payload"]) as e:
+                e.init_chains()
+                e.step_rounds(W * R - 1)
+                e.sync()
+                w_ms, _, _, w_acc, _ = timed_steps(e, K, R, per_launch=False)
+            out["modes"] = {"welford": {
+                "value": S * T * K * R / (w_ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": w_ms / K,
+                "accept_rate_timed_region": [float(v) for v in w_acc],
+                "note": "gpu.shaper \"welford\": second-moment matrix updated per element on an accept, re-Cholesky at the adapt points; "
+                        "NOT the reference's arithmetic (no bit parity; tests/test_welford_gpu.py validates it statistically); the "
+                        "headline above is the reference-exact mode"}}
+        except Exception as ex:
+            sys.stderr.write("welford mode arm failed (%r)\n" % (ex,))
     if not args.no_ess:
         eps = ess_per_cold_sample(local_rank)
         out["ess"] = {"ess_per_cold_sample": eps, "ess_per_sec": eps * value / T,

@@ -299,6 +299,14 @@ __global__ void __launch_bounds__(SLGPU_THREADS) pt_init_kernel(const slgpu_step
   for (int r = 0; r < d; ++r)
     for (int k = 0; k <= r; ++k)
       l_elem(p.L, p.n_temps, m.s, (u32)m.t, d, r, k) = (r == k) ? (p.mx[r] - p.mn[r]) / 4.0 : 0.0;
+  if (p.moment) { /* "gpu": {"shaper": "welford"}: the second moment behind the initial factor, L0 L0^T = diag(range^2) */
+    for (int r = 0; r < d; ++r)
+      for (int k = 0; k <= r; ++k) {
+        const double rg = (p.mx[r] - p.mn[r]) / 4.0;
+        l_elem(p.moment, p.n_temps, m.s, (u32)m.t, d, r, k) = (r == k) ? rg * rg : 0.0;
+      }
+    p.chol_dirty[c] = 0;
+  }
   const double b = p.ladder[m.t];
   p.energy[c] = e;
   p.row_sigma[c] = 1.0;
@@ -633,7 +641,7 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
     constexpr int JS = StaticJobs<Lik, D>::value;
     if (!(JS > 0 && p->n_job_types != (uint32_t)JS)) {
       constexpr int NT = SLGPU_FAST_THREADS;
-      auto kern = pt_step_fast_kernel<Lik, D, NT>;
+      auto kern = p->moment ? pt_step_fast_kernel<Lik, D, NT, true> : pt_step_fast_kernel<Lik, D, NT, false>;
       const size_t smem = fast_smem_bytes<D, NT>(p->n_temps);
       /* the opt-in is per device and context: set it on every launch (a process may drive several devices) */
       const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<D, NT>(1));
@@ -657,6 +665,25 @@ int launch_step_t(const slgpu_step_params* p, void* stream) {
   pt_step_kernel<Lik, D><<<grid_for(p), SLGPU_THREADS, 0, (cudaStream_t)stream>>>(*p);
   return (int)cudaGetLastError();
 }
+/* "gpu": {"shaper": "welford"}: re-factorise the dirty chains' moment matrices (rechol_kernel); only the thread-per-chain
+ * kernel of a specialised dimension <= 32 keeps moments */
+template <int D>
+int launch_rechol_t(const slgpu_step_params* p, void* stream) {
+#ifndef SLGPU_TILE_KERNEL
+  if constexpr (D > 0 && D <= 32) {
+    if (p->moment) {
+      const size_t smem = ((size_t)D * (D + 1) / 2 + D) * 32 * sizeof(double);
+      auto kern = rechol_kernel<D>;
+      const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (attr != cudaSuccess) return (int)attr;
+      const unsigned spw = 32u / p->n_temps;
+      kern<<<(p->n_stacks + spw - 1) / spw, 32, smem, (cudaStream_t)stream>>>(*p);
+      return (int)cudaGetLastError();
+    }
+  }
+#endif
+  return (int)cudaErrorNotSupported;
+}
 template <class Lik>
 int launch_eval_t(const slgpu_step_params* p, const double* x, uint32_t n_points, double* nll, void* stream) {
   if (n_points == 0) return 0;
@@ -677,6 +704,12 @@ struct Dispatch {
     const bool hit = ((p->n_dims == (uint32_t)Ds ? (rc = launch_step_t<Lik, Ds>(p, s), true) : false) || ...);
     return hit ? rc : launch_step_t<Lik, 0>(p, s);
   }
+  static int rechol(const slgpu_step_params* p, void* s) {
+    int rc = (int)cudaErrorNotSupported;
+    const bool hit = ((p->n_dims == (uint32_t)Ds ? (rc = launch_rechol_t<Ds>(p, s), true) : false) || ...);
+    (void)hit;
+    return rc;
+  }
 };
 
 }  // namespace slgpu
@@ -689,9 +722,10 @@ struct Dispatch {
   static int sym##_eval(const slgpu_step_params* p, const double* x, uint32_t n, double* o, void* s) {            \
     return slgpu::launch_eval_t<Lik>(p, x, n, o, s);                                                              \
   }                                                                                                               \
+  static int sym##_rechol(const slgpu_step_params* p, void* s) { return slgpu::Dispatch<Lik, ##__VA_ARGS__>::rechol(p, s); } \
   extern "C" const slgpu_plugin_v1* sym(void) {                                                                   \
     static const slgpu_plugin_v1 table = {SLGPU_PLUGIN_ABI, plugin_name, n_jobs, n_dims_fixed, payload_size,      \
-                                          sym##_init,       sym##_step,  sym##_eval};                             \
+                                          sym##_init,       sym##_step,  sym##_eval, sym##_rechol};               \
     return &table;                                                                                                \
   }
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SLGPU_PLUGIN_ABI 4u
+#define SLGPU_PLUGIN_ABI 5u
 #define SLGPU_MAX_DIMS 128u  /* largest nDims the generic (runtime-d) kernels accept */
 #define SLGPU_MAX_TEMPS 32u  /* a stack's temperature ladder lives in one warp */
 #define SLGPU_L_TILE 32u    /* chain slots per tile of the packed-L store (see slgpu_step_params.L) */
@@ -37,6 +37,7 @@ extern "C" {
   (SLGPU_L_LAYOUT(n_dims) == SLGPU_L_COLMAJOR                                                                           \
        ? (((size_t)(n_stacks) * (n_temps) + 127u) / 128u * 128u) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u)           \
        : (size_t)(((n_stacks) + 32u / (n_temps) - 1u) / (32u / (n_temps))) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u) * SLGPU_L_TILE)
+#define SLGPU_JUMP_LOG_SLOTS 16u /* "gpu": {"shaper": "welford"}: accepted jumps a chain can log between two adapt points */
 #define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
 
 enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
@@ -107,6 +108,14 @@ typedef struct slgpu_step_params {
   const double* rp_uswap;
   const double* rp_xinit;
   const void* payload;     /* the plugin's POD payload, copied to the device by the engine */
+  /* "gpu": {"shaper": "welford"} -- NOT the reference's arithmetic, off by default (moment == NULL): the second moment of the
+   * accepted jumps is kept as a matrix, moment[] in the layout of L.  An accept only appends its jump vector to the chain's
+   * log, jump_log[(slot * d + i) * C + chain] with slot = chol_dirty[chain]++ (at most SLGPU_JUMP_LOG_SLOTS between two adapt
+   * points); launch_rechol, at the adapt points, folds the logged jumps into the matrix (C <- (n-1)/n C + s s^T / n, the
+   * recurrence L L^T follows in adaptive.cpp:173-197) and re-factorises L from it. */
+  double* moment;
+  double* jump_log;
+  unsigned char* chol_dirty; /* [C] jumps logged since the last re-Cholesky */
 } slgpu_step_params;
 
 /* Launchers return a cudaError_t value (0 = success); stream is a cudaStream_t. */
@@ -122,6 +131,9 @@ typedef struct slgpu_plugin_v1 {
   int (*launch_step)(const slgpu_step_params* p, void* stream);
   /* nll[point * J + job] = f(job, x[point * d ..]) for n_points points (point-major x): contract check */
   int (*launch_eval)(const slgpu_step_params* p, const double* x, uint32_t n_points, double* nll, void* stream);
+  /* "gpu": {"shaper": "welford"} only: L = chol(moment), nscale = prop_norm / |L|_F for the chains marked dirty.  Returns
+   * cudaErrorNotSupported when the plugin has no Welford kernels for this dimension. */
+  int (*launch_rechol)(const slgpu_step_params* p, void* stream);
 } slgpu_plugin_v1;
 
 typedef const slgpu_plugin_v1* (*slgpu_plugin_entry_fn)(void);

@@ -282,7 +282,12 @@ inline size_t fast_smem_bytes(unsigned n_temps) {
   return ((size_t)2 * D * NT + (size_t)D * (NT + 1) + (size_t)2 * D * nsb) * sizeof(double) + SLGPU_FAST_SMEM_PAD;
 }
 
-template <class Lik, int D, int NT>
+/* WELFORD = false: the reference's ProposalShaper (rank-1 Cholesky update on every accept), bit for bit.
+ * WELFORD = true ("gpu": {"shaper": "welford"}, NOT the reference's arithmetic): on an accept the thread updates the second-moment
+ * matrix of its chain element by element -- no serial column sweep, no staging, no block barrier in the round -- and the
+ * factor is re-computed between launches (rechol_kernel).  north_star's "Welford rank-1 covariance update with periodic
+ * re-Cholesky", validated statistically only (tests/test_welford_gpu.py). */
+template <class Lik, int D, int NT, bool WELFORD = false>
 __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(const slgpu_step_params p) {
   const u32 blk = blockIdx.x; /* stack group of this block */
   const ThreadMap m(p, blk);
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
   int accepted = p.accepted[c], swap_type = p.swap_type[c];
   u32 lg_accepts = p.lg_accepts[c], lg_swaps = p.lg_swaps[c], lg_att = p.lg_swap_attempts[c];
   double lg_min_e = p.lg_min_energy[c];
+  int n_logged = WELFORD ? (int)p.chol_dirty[c] : 0; /* jumps of this chain waiting for the next re-Cholesky */
   double w3[3] = {0.0, 0.0, 0.0};
   const int W = (int)p.swap_interval;
   SLGPU_STAMP(1);
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     bool acc = false;
     /* ================= phase A: propose, evaluate, accept, sigma ================= */
     if (active) {
-      const bool fresh = (sh_count == p.sh_count0);
+      const bool fresh = WELFORD ? (nscale == 0.0) : (sh_count == p.sh_count0); /* N still the constructor's diag(range/|range|) */
       const double* zr = replay ? p.rp_z + ((size_t)r * C + c) * D : nullptr;
       double a[D];
 #pragma unroll
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
         acc = u < slm_exp(-1.0 * beta * deltaEnergy);
       }
       if (acc) {
-        const int slot = atomicAdd(&s_nacc[par], 1);
+        const int slot = WELFORD ? tid : atomicAdd(&s_nacc[par], 1); /* WELFORD: every chain updates its own moment matrix */
         sh_count += 1.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -405,8 +411,15 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
           s_jump[i * NT + slot] = nx - s_x[i * NX + tid]; /* the accepted jump (sampler.cpp:166) */
           s_x[i * NX + tid] = nx;
         }
-        s_cnt[slot] = sh_count;
-        s_owner[slot] = (unsigned short)tid;
+        if constexpr (WELFORD) {
+          /* the jump goes to the chain's log; rechol_kernel folds it into the second-moment matrix at the next adapt point */
+#pragma unroll
+          for (int i = 0; i < D; ++i) __stcs(p.jump_log + ((size_t)n_logged * D + i) * C + c, s_jump[i * NT + tid]);
+          n_logged += 1;
+        } else {
+          s_cnt[slot] = sh_count;
+          s_owner[slot] = (unsigned short)tid;
+        }
         energy = e_new;
         row_sigma = sigma;
         row_beta = beta;
@@ -429,6 +442,7 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
       stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
       sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
     }
+    if constexpr (!WELFORD) {
     __syncthreads();
     SLGPU_STAMP(2 + 3 * it);
     /* ================= phase B: compacted ProposalShaper updates ================= */
@@ -474,6 +488,9 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     __syncthreads();
     SLGPU_STAMP(3 + 3 * it);
     if (acc) nscale = s_nsc[tid];
+    } else {
+      if (it == 0) __syncthreads(); /* s_lad (loaded behind the grid dependency in round 0) is read in the swap sweep */
+    }
     /* the table logger's per-round log: written here, where acc dies; the swap sweep below adds its two bits */
 #ifndef SLGPU_STAMPS
     if (p.round_flags && active) p.round_flags[(size_t)it * C + c] = (unsigned char)(acc ? 1 : 0);
@@ -592,7 +609,8 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
     p.row_beta[c] = row_beta;
     p.sigma[c] = sigma;
     p.beta[c] = beta;
-    p.nscale[c] = nscale;
+    if constexpr (WELFORD) p.chol_dirty[c] = (unsigned char)n_logged; /* and rechol_kernel owns nscale */
+    else p.nscale[c] = nscale;
     p.sh_count[c] = sh_count;
     p.accepted[c] = accepted;
     p.swap_type[c] = swap_type;
@@ -603,6 +621,67 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #pragma unroll
     for (int k = 0; k < 9; ++k) p.p_sig[pidx(p, k, m.t, m.s)] = Ps[k];
   }
+}
+
+/* "gpu": {"shaper": "welford"}, at the adapt points: for every chain that logged accepted jumps, fold them into its
+ * second-moment matrix in the order they happened -- C <- (n-1)/n C + s s^T / n with n the shaper count after that accept,
+ * the recurrence L L^T obeys under ProposalShaper::update (adaptive.cpp:179-197) -- then L = chol(C) and
+ * nscale = prop_norm / |L|_F (adaptive.cpp:200).  One warp per stack group: the group's tile is staged in shared memory, thread
+ * per chain.  Plain left-looking Cholesky; a non-positive pivot (rounding only: C is a positive diagonal plus outer products)
+ * is floored. */
+template <int D>
+__global__ void __launch_bounds__(32) rechol_kernel(const slgpu_step_params p) {
+  constexpr int NL = D * (D + 1) / 2;
+  extern __shared__ double s_t[]; /* [NL][32] the tile, then [D][32] the jump being folded */
+  const int lane = threadIdx.x;
+  const int T = (int)p.n_temps, spw = 32 / T, sl = lane / T;
+  const u32 s = blockIdx.x * (u32)spw + (u32)sl;
+  const bool active = sl < spw && s < p.n_stacks;
+  const u32 c = active ? s * (u32)T + (u32)(lane - sl * T) : 0u;
+  const size_t C = (size_t)p.n_stacks * p.n_temps;
+  const int n_logged = active ? (int)p.chol_dirty[c] : 0;
+  if (!__any_sync(0xffffffffu, n_logged > 0)) return;
+  double* Cg = p.moment + (size_t)blockIdx.x * NL * 32;
+  for (int i = 0; i < NL; ++i) s_t[i * 32 + lane] = Cg[(size_t)i * 32 + lane];
+  if (n_logged == 0) return;
+  double* A = s_t + lane;           /* A[idx * 32] */
+  double* sj = s_t + NL * 32 + lane; /* sj[i * 32] */
+  const double cnt = p.sh_count[c];
+  for (int q = 0; q < n_logged; ++q) {
+    const double n = cnt - (double)(n_logged - 1 - q);
+    const double fold = (n - 1.0) / n, rn = 1.0 / n;
+    for (int i = 0; i < D; ++i) sj[i * 32] = p.jump_log[((size_t)q * D + i) * C + c];
+    for (int j = 0; j < D; ++j) {
+      const double sjn = sj[j * 32] * rn;
+      for (int k = 0; k <= j; ++k) {
+        double* e = A + (j * (j + 1) / 2 + k) * 32;
+        *e = fma(sjn, sj[k * 32], *e * fold);
+      }
+    }
+  }
+  for (int i = 0; i < NL; ++i) Cg[(size_t)i * 32 + lane] = A[i * 32]; /* the moment matrix itself, before it is factorised in place */
+  double frob = 0.0;
+  for (int k = 0; k < D; ++k) {
+    const int rk = k * (k + 1) / 2;
+    double v = A[(rk + k) * 32];
+    for (int mm = 0; mm < k; ++mm) v = fma(-A[(rk + mm) * 32], A[(rk + mm) * 32], v);
+    const double lkk = sqrt(smax(v, 1e-300));
+    const double rl = 1.0 / lkk;
+    A[(rk + k) * 32] = lkk;
+    frob = fma(lkk, lkk, frob);
+    for (int j = k + 1; j < D; ++j) {
+      const int rj = j * (j + 1) / 2;
+      double w = A[(rj + k) * 32];
+      for (int mm = 0; mm < k; ++mm) w = fma(-A[(rj + mm) * 32], A[(rk + mm) * 32], w);
+      w *= rl;
+      A[(rj + k) * 32] = w;
+      frob = fma(w, w, frob);
+    }
+  }
+  double* Lg = p.L + (size_t)blockIdx.x * NL * 32 + lane;
+  for (int i = 0; i < NL; ++i) Lg[(size_t)i * 32] = A[i * 32];
+  p.nscale[c] = p.prop_norm / smax(sqrt(frob), 1e-18);
+  p.chol_dirty[c] = 0;
 }
 
 }  // namespace slgpu

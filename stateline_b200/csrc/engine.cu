@@ -83,6 +83,7 @@ struct Settings {
   bool windowRates = false;  // keep the adapters' windowed accept / swap rates (the AcptRt / SwapRt columns of the table logger)
   uint32_t csvThreads = 0;  // csv sink: formatter threads (0 = one per host core, at most 16)
   bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
+  bool welford = false;  // "shaper": "welford": second-moment matrix + periodic re-Cholesky (NOT the reference's update; opt-in)
 };
 
 struct Segment {
@@ -292,6 +293,12 @@ Settings parse_settings(const char* text) {
     if (g->find("windowRates")) s.windowRates = need(*g, "windowRates", slgpu_json::Value::Bool).b;
     if (g->find("csvThreads")) s.csvThreads = (uint32_t)need_uint(*g, "csvThreads");
     if (g->find("append")) s.append = need(*g, "append", slgpu_json::Value::Bool).b;
+    if (g->find("shaper")) {
+      const std::string& k = need(*g, "shaper", slgpu_json::Value::String).str;
+      if (k == "reference") s.welford = false;
+      else if (k == "welford") s.welford = true;
+      else throw ConfigError{"gpu.shaper must be \"reference\" or \"welford\""};
+    }
     if (g->find("wire")) {
       const std::string& k = need(*g, "wire", slgpu_json::Value::String).str;
       if (k == "delta") s.wire = WIRE_DELTA;
@@ -829,6 +836,15 @@ slgpu_status adapt_point(slgpu_engine* e) {
                                                                   e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
   CU_TRY(cudaGetLastError());
   e->launches += 1;
+  if (e->cfg.welford) {  // the periodic re-Cholesky: at the adapt points (a schedule in rounds, not in launches), for the chains an accept has marked
+    const int rc2 = e->plug->launch_rechol ? e->plug->launch_rechol(&e->P, (void*)e->compute) : (int)cudaErrorNotSupported;
+    if (rc2 != 0) {
+      e->failed = true;
+      return fail(rc2 == (int)cudaErrorNotSupported ? SLGPU_E_PLUGIN : SLGPU_E_CUDA,
+                  std::string("launch_rechol: ") + (rc2 == (int)cudaErrorNotSupported ? "the plugin has no Welford kernels for this dimension (list it in SLGPU_DEFINE_PLUGIN)" : cudaGetErrorString((cudaError_t)rc2)));
+    }
+    e->launches++;
+  }
   return SLGPU_OK;
 }
 
@@ -964,6 +980,15 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
     const size_t nLall = SLGPU_L_DOUBLES(S, T, d);
     TRY_ST(dev_alloc(e, &P.L, nLall));
     CU_TRY(cudaMemset(P.L, 0, nLall * sizeof(double)));  // the idle slots of a tile travel with it: keep them defined
+    if (cfg.welford) {
+      if (d > 32 || cfg.sequential || cfg.adaptInterval > SLGPU_JUMP_LOG_SLOTS)
+        return fail(SLGPU_E_CONFIG, "gpu.shaper \"welford\" needs nDims <= 32, the batched schedule and adaptInterval <= " + std::to_string(SLGPU_JUMP_LOG_SLOTS));
+      TRY_ST(dev_alloc(e, &P.jump_log, (size_t)cfg.adaptInterval * d * C));
+      TRY_ST(dev_alloc(e, &P.moment, nLall));
+      CU_TRY(cudaMemset(P.moment, 0, nLall * sizeof(double)));
+      TRY_ST(dev_alloc(e, &P.chol_dirty, C));
+      CU_TRY(cudaMemset(P.chol_dirty, 0, C));
+    }
     TRY_ST(dev_alloc(e, &P.energy, C)); TRY_ST(dev_alloc(e, &P.row_sigma, C)); TRY_ST(dev_alloc(e, &P.row_beta, C));
     TRY_ST(dev_alloc(e, &P.sigma, C)); TRY_ST(dev_alloc(e, &P.beta, C)); TRY_ST(dev_alloc(e, &P.nscale, C));
     TRY_ST(dev_alloc(e, &P.sh_count, C));
@@ -990,6 +1015,11 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
                   {"ep_m", P.ep_m, (size_t)d * S * f8}, {"ep_s", P.ep_s, (size_t)d * S * f8},
                   {"models", e->d_models, (size_t)2 * T * slgpu_tier::kModelStride * f8}, {"sig_w", e->d_sig_w, (size_t)3 * T * f8},
                   {"ladder", e->d_ladder, T * f8}};
+    }
+    if (cfg.welford) {
+      e->state.push_back({"moment", P.moment, nLall * sizeof(double)});
+      e->state.push_back({"chol_dirty", P.chol_dirty, C});
+      e->state.push_back({"jump_log", P.jump_log, (size_t)cfg.adaptInterval * d * C * sizeof(double)});
     }
     if (payload && payload_bytes) {
       TRY_ST(dev_alloc(e, (char**)&e->d_payload, payload_bytes));
@@ -1476,7 +1506,7 @@ slgpu_status slgpu_get_shaper(slgpu_engine* e, uint32_t chain, double* L, double
   CU_TRY(cudaMemcpy(&cnt, e->P.sh_count + chain, sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(&ns, e->P.nscale + chain, sizeof(double), cudaMemcpyDeviceToHost));
   if (count) *count = cnt;
-  const bool fresh = (cnt == e->P.sh_count0);
+  const bool fresh = e->cfg.welford ? (ns == 0.0) : (cnt == e->P.sh_count0);
   for (size_t r = 0; r < d; ++r)
     for (size_t k = 0; k < d; ++k) {
       const double l = (k <= r) ? packed[r * (r + 1) / 2 + k] : 0.0;
