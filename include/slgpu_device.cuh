@@ -672,12 +672,12 @@ int launch_rechol_t(const slgpu_step_params* p, void* stream) {
 #ifndef SLGPU_TILE_KERNEL
   if constexpr (D > 0 && D <= 32) {
     if (p->moment) {
-      const size_t smem = ((size_t)D * (D + 1) / 2 + D) * 32 * sizeof(double);
+      const size_t smem = ((size_t)D * (D + 1) / 2 + D + kRecholWarps) * 32 * sizeof(double);
       auto kern = rechol_kernel<D>;
       const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (attr != cudaSuccess) return (int)attr;
       const unsigned spw = 32u / p->n_temps;
-      kern<<<(p->n_stacks + spw - 1) / spw, 32, smem, (cudaStream_t)stream>>>(*p);
+      kern<<<(p->n_stacks + spw - 1) / spw, kRecholWarps * 32, smem, (cudaStream_t)stream>>>(*p);
       return (int)cudaGetLastError();
     }
   }

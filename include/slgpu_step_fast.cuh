@@ -20,6 +20,8 @@
 #ifndef SLGPU_STEP_FAST_CUH
 #define SLGPU_STEP_FAST_CUH
 
+#include "slgpu_bulk.cuh"
+
 namespace slgpu {
 
 #ifndef SLGPU_FAST_MINBLOCKS
@@ -626,62 +628,138 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 /* "gpu": {"shaper": "welford"}, at the adapt points: for every chain that logged accepted jumps, fold them into its
  * second-moment matrix in the order they happened -- C <- (n-1)/n C + s s^T / n with n the shaper count after that accept,
  * the recurrence L L^T obeys under ProposalShaper::update (adaptive.cpp:179-197) -- then L = chol(C) and
- * nscale = prop_norm / |L|_F (adaptive.cpp:200).  One warp per stack group: the group's tile is staged in shared memory, thread
- * per chain.  Plain left-looking Cholesky; a non-positive pivot (rounding only: C is a positive diagonal plus outer products)
- * is floored. */
+ * nscale = prop_norm / |L|_F (adaptive.cpp:200).  One block per stack group: its tile of 32 matrices is staged in shared
+ * memory; lane = chain, and the kRecholWarps warps split the matrix ROWS (row j belongs to warp j % kRecholWarps), so every
+ * shared-memory access is a full 32-lane row of the tile and a thread carries several independent dot products.  Left-looking
+ * Cholesky: the owner of row k publishes the pivot, a barrier, every warp scales its rows.  A non-positive pivot (rounding
+ * only: C is a positive diagonal plus outer products) is floored. */
+#ifndef SLGPU_RECHOL_WARPS
+#define SLGPU_RECHOL_WARPS 4
+#endif
+constexpr int kRecholWarps = SLGPU_RECHOL_WARPS;
 template <int D>
-__global__ void __launch_bounds__(32) rechol_kernel(const slgpu_step_params p) {
+__global__ void __launch_bounds__(kRecholWarps * 32) rechol_kernel(const slgpu_step_params p) {
   constexpr int NL = D * (D + 1) / 2;
-  extern __shared__ double s_t[]; /* [NL][32] the tile, then [D][32] the jump being folded */
-  const int lane = threadIdx.x;
+  constexpr int NW = kRecholWarps;
+  constexpr int RPT = (D + NW - 1) / NW; /* rows per thread */
+  extern __shared__ double s_t[];        /* [NL][32] the tile, [D][32] the jump being folded (then the new diagonal), [NW][32] partial norms */
+  double* s_j = s_t + NL * 32;
+  double* s_fr = s_j + D * 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int T = (int)p.n_temps, spw = 32 / T, sl = lane / T;
   const u32 s = blockIdx.x * (u32)spw + (u32)sl;
   const bool active = sl < spw && s < p.n_stacks;
   const u32 c = active ? s * (u32)T + (u32)(lane - sl * T) : 0u;
   const size_t C = (size_t)p.n_stacks * p.n_temps;
   const int n_logged = active ? (int)p.chol_dirty[c] : 0;
-  if (!__any_sync(0xffffffffu, n_logged > 0)) return;
+  const int n_max = __reduce_max_sync(0xffffffffu, n_logged); /* every warp sees the same 32 chains */
+  if (n_max == 0) return;
   double* Cg = p.moment + (size_t)blockIdx.x * NL * 32;
-  for (int i = 0; i < NL; ++i) s_t[i * 32 + lane] = Cg[(size_t)i * 32 + lane];
-  if (n_logged == 0) return;
-  double* A = s_t + lane;           /* A[idx * 32] */
-  double* sj = s_t + NL * 32 + lane; /* sj[i * 32] */
-  const double cnt = p.sh_count[c];
-  for (int q = 0; q < n_logged; ++q) {
-    const double n = cnt - (double)(n_logged - 1 - q);
-    const double fold = (n - 1.0) / n, rn = 1.0 / n;
-    for (int i = 0; i < D; ++i) sj[i * 32] = p.jump_log[((size_t)q * D + i) * C + c];
-    for (int j = 0; j < D; ++j) {
-      const double sjn = sj[j * 32] * rn;
-      for (int k = 0; k <= j; ++k) {
-        double* e = A + (j * (j + 1) / 2 + k) * 32;
-        *e = fma(sjn, sj[k * 32], *e * fold);
+  double* Lg = p.L + (size_t)blockIdx.x * NL * 32;
+  __shared__ unsigned long long s_bar;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, NL * 32 * (unsigned)sizeof(double));
+    bulk_load(s_t, Cg, NL * 32 * (unsigned)sizeof(double), &s_bar); /* the whole tile in one bulk copy */
+  }
+  double* A = s_t + lane; /* this chain's matrix: A[idx * 32] */
+  const double cnt = active ? p.sh_count[c] : 1.0;
+  double nxt[RPT]; /* the rows this warp stages of the NEXT logged jump: its load is in flight while the current one is folded */
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int i = wid + r * NW;
+    nxt[r] = (i < D && 0 < n_logged) ? __ldcs(p.jump_log + (size_t)i * C + c) : 0.0;
+  }
+  for (int q = 0; q < n_max; ++q) {
+    if (q) __syncthreads(); /* the previous jump has been consumed */
+    const bool has = q < n_logged;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int i = wid + r * NW;
+      if (i < D) s_j[i * 32 + lane] = nxt[r];
+      nxt[r] = (i < D && q + 1 < n_logged) ? __ldcs(p.jump_log + ((size_t)(q + 1) * D + i) * C + c) : 0.0;
+    }
+    __syncthreads();
+    if (q == 0) mbar_wait(&s_bar, 0);
+    if (has) {
+      const double n = cnt - (double)(n_logged - 1 - q);
+      const double fold = (n - 1.0) / n, rn = 1.0 / n;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int j = wid + r * NW;
+        if (j < D) {
+          const double sjn = s_j[j * 32 + lane] * rn;
+          double* e = A + (j * (j + 1) / 2) * 32;
+          int k = 0;
+          for (; k + 4 <= j + 1; k += 4) { /* four independent elements at a time */
+            const double e0 = e[k * 32], e1 = e[(k + 1) * 32], e2 = e[(k + 2) * 32], e3 = e[(k + 3) * 32];
+            const double s0 = s_j[k * 32 + lane], s1 = s_j[(k + 1) * 32 + lane], s2 = s_j[(k + 2) * 32 + lane], s3 = s_j[(k + 3) * 32 + lane];
+            e[k * 32] = fma(sjn, s0, e0 * fold);
+            e[(k + 1) * 32] = fma(sjn, s1, e1 * fold);
+            e[(k + 2) * 32] = fma(sjn, s2, e2 * fold);
+            e[(k + 3) * 32] = fma(sjn, s3, e3 * fold);
+          }
+          for (; k <= j; ++k) e[k * 32] = fma(sjn, s_j[k * 32 + lane], e[k * 32] * fold);
+        }
       }
     }
   }
-  for (int i = 0; i < NL; ++i) Cg[(size_t)i * 32 + lane] = A[i * 32]; /* the moment matrix itself, before it is factorised in place */
+  __syncthreads();
+  const bool redo = n_logged > 0;
+  if (redo)
+    for (int i = wid; i < NL; i += NW) Cg[(size_t)i * 32 + lane] = A[i * 32]; /* the moment matrix itself, before it is factorised in place */
+  __syncthreads();
   double frob = 0.0;
   for (int k = 0; k < D; ++k) {
     const int rk = k * (k + 1) / 2;
-    double v = A[(rk + k) * 32];
-    for (int mm = 0; mm < k; ++mm) v = fma(-A[(rk + mm) * 32], A[(rk + mm) * 32], v);
-    const double lkk = sqrt(smax(v, 1e-300));
+    /* the rows of this thread below the diagonal of column k: their dot products with row k advance together, and so does
+     * row k's own (the pivot), which every thread carries for itself */
+    double acc[RPT];
+    int rowoff[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      int j = wid + r * NW;
+      if (j >= D || j <= k) j = k; /* a spare slot repeats row k: valid addresses, its result is not used */
+      rowoff[r] = (j * (j + 1) / 2) * 32;
+      acc[r] = A[rowoff[r] + k * 32];
+    }
+    double piv = A[(rk + k) * 32];
+    for (int m = 0; m < k; ++m) {
+      const double akm = A[(rk + m) * 32];
+      piv = fma(-akm, akm, piv);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) acc[r] = fma(-A[rowoff[r] + m * 32], akm, acc[r]);
+    }
+    const double lkk = sqrt(smax(piv, 1e-300));
     const double rl = 1.0 / lkk;
-    A[(rk + k) * 32] = lkk;
-    frob = fma(lkk, lkk, frob);
-    for (int j = k + 1; j < D; ++j) {
-      const int rj = j * (j + 1) / 2;
-      double w = A[(rj + k) * 32];
-      for (int mm = 0; mm < k; ++mm) w = fma(-A[(rj + mm) * 32], A[(rk + mm) * 32], w);
-      w *= rl;
-      A[(rj + k) * 32] = w;
-      frob = fma(w, w, frob);
+    if ((k % NW) == wid) {
+      s_j[k * 32 + lane] = lkk; /* parked beside the tile: the other warps may still be reading C[k][k] */
+      frob = fma(lkk, lkk, frob);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int j = wid + r * NW;
+      if (j > k && j < D) {
+        const double w = acc[r] * rl;
+        A[rowoff[r] + k * 32] = w;
+        frob = fma(w, w, frob);
+      }
+    }
+    __syncthreads();
+  }
+  s_fr[wid * 32 + lane] = frob;
+  for (int k = wid; k < D; k += NW) A[(k * (k + 1) / 2 + k) * 32] = s_j[k * 32 + lane];
+  __syncthreads();
+  if (redo) {
+    for (int i = wid; i < NL; i += NW) Lg[(size_t)i * 32 + lane] = A[i * 32];
+    if (wid == 0) {
+      double f = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) f += s_fr[w * 32 + lane];
+      p.nscale[c] = p.prop_norm / smax(sqrt(f), 1e-18);
+      p.chol_dirty[c] = 0;
     }
   }
-  double* Lg = p.L + (size_t)blockIdx.x * NL * 32 + lane;
-  for (int i = 0; i < NL; ++i) Lg[(size_t)i * 32] = A[i * 32];
-  p.nscale[c] = p.prop_norm / smax(sqrt(frob), 1e-18);
-  p.chol_dirty[c] = 0;
 }
 
 }  // namespace slgpu
