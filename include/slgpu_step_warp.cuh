@@ -43,23 +43,25 @@ inline size_t warp_smem_bytes(const slgpu_step_params* p, unsigned warps, bool w
 inline unsigned warp_stacks_per_block(unsigned n_temps) { return n_temps >= 8 ? 1u : 8u / n_temps; }
 
 /* ---- column sweeps of the warp kernel.  Lp = Lg + lane; off_k = ck - k (ck = k*d - k(k-1)/2), so that L(j,k) with
- * j = lane + 32m is Lp[off_k + 32m] and off_{k+1} = off_k + d - k - 1.  The sweeps are cut at the row-group
+ * j = lane + 32m is Lp[off_k + 32m] and off_{k+1} = off_k + d - k - 1: a sweep carries the pointer Lp + off_k from column to
+ * column and addresses the row groups with immediate offsets.  The sweeps are cut at the row-group
  * boundaries (columns 32G .. 32G+31) so that which row groups take part is known at compile time. ---- */
 
-/* raw column k, rows j >= k of this lane (0 elsewhere); any k */
+/* raw column k, rows j >= k of this lane (0 elsewhere); any k.  pc = Lp + off_k */
 template <int RM>
-__device__ __forceinline__ void warp_load_col(double* dst, const double* Lp, int off, int k, int lane, int d) {
+__device__ __forceinline__ void warp_load_col(double* dst, const double* pc, int k, int lane, int d) {
 #pragma unroll
   for (int m = 0; m < RM; ++m) {
     const int j = lane + 32 * m;
-    dst[m] = (32 * m + 31 >= k && j >= k && j < d) ? Lp[off + 32 * m] : 0.0;
+    dst[m] = (32 * m + 31 >= k && j >= k && j < d) ? pc[32 * m] : 0.0;
   }
 }
 
-/* proposal GEMV, columns of row group G: a_j = fma(N_jk, z_k, a_j), k ascending */
+/* proposal GEMV, columns of row group G: a_j = fma(N_jk, z_k, a_j), k ascending.  pc walks the columns (pc = Lp + off_k):
+ * the loads of a column are pc[32 m] with immediate offsets */
 template <int RM, int G>
-__device__ __forceinline__ void warp_gemv_group(const double* Lp, int& off, const double* vec, const double* s_n0, double nscale,
-                                                bool fresh, int lane, int d, double* a) {
+__device__ __forceinline__ void warp_gemv_group(const double*& pc, const double* vec, const double* s_n0, double nscale, bool fresh,
+                                                int lane, int d, double* a) {
   const int k1 = (32 * G + 32 < d) ? 32 * G + 32 : d;
 #pragma unroll kWarpGemvUnroll
   for (int k = 32 * G; k < k1; ++k) {
@@ -69,15 +71,15 @@ __device__ __forceinline__ void warp_gemv_group(const double* Lp, int& off, cons
     for (int m = G; m < RM; ++m) {
       const int j = lane + 32 * m;
       if ((m > G || j >= k) && j < d) {
-        double njk = Lp[off + 32 * m] * nscale;
+        double njk = pc[32 * m] * nscale;
         if (m == G && j == k) njk = fresh ? n0k : njk + 1e-4;
         a[m] = fma(njk, zk, a[m]);
       }
     }
-    off += d - k - 1;
+    pc += d - k - 1;
   }
   if constexpr (G + 1 < RM) {
-    if (k1 < d) warp_gemv_group<RM, G + 1>(Lp, off, vec, s_n0, nscale, fresh, lane, d, a);
+    if (k1 < d) warp_gemv_group<RM, G + 1>(pc, vec, s_n0, nscale, fresh, lane, d, a);
   }
 }
 
@@ -85,15 +87,15 @@ __device__ __forceinline__ void warp_gemv_group(const double* Lp, int& off, cons
  * columns k and k+1 (loaded two columns ahead of their use: a column's loads never depend on earlier columns'
  * stores); the column head (old diagonal, x_k) comes from the owning lane by shuffle, not from memory. */
 template <int RM, int G>
-__device__ __forceinline__ void warp_shaper_group(double* Lp, int& off, int& off1, double* cur, double* nx1, double scale, int lane, int d,
+__device__ __forceinline__ void warp_shaper_group(double*& p0, double*& p1, double* cur, double* nx1, double scale, int lane, int d,
                                                   double* xs, double* fr) {
   const double eps = 1e-18;
   const int k1 = (32 * G + 32 < d) ? 32 * G + 32 : d;
 #pragma unroll 1
   for (int k = 32 * G; k < k1; ++k) {
     double nx2[RM];
-    const int off2 = off1 + d - k - 2;
-    warp_load_col<RM>(nx2, Lp, off2, (k + 2 < d) ? k + 2 : 0x7fff, lane, d); /* past the last column: nothing is loaded */
+    double* const p2 = p1 + (d - k - 2);
+    warp_load_col<RM>(nx2, p2, (k + 2 < d) ? k + 2 : 0x7fff, lane, d); /* past the last column: nothing is loaded */
     const double xk = __shfl_sync(0xffffffffu, xs[G], k & 31);
     const double Lkk = __shfl_sync(0xffffffffu, cur[G], k & 31) * scale;
     const double V = smax(eps, Lkk);
@@ -107,12 +109,12 @@ __device__ __forceinline__ void warp_shaper_group(double* Lp, int& off, int& off
       const int j = lane + 32 * m;
       if (j < d) {
         if (m == G && j == k) {
-          Lp[off + 32 * m] = rr;
+          p0[32 * m] = rr;
           fr[m] = fma(rr, rr, fr[m]); /* the diagonal closes row k's sum */
         } else if (m > G || j > k) {
           double Ljk = cur[m] * scale;
           Ljk = div_by(Ljk + ss * xs[m], cc, rc);
-          Lp[off + 32 * m] = Ljk;
+          p0[32 * m] = Ljk;
           xs[m] = cc * xs[m] - ss * Ljk;
           fr[m] = fma(Ljk, Ljk, fr[m]);
         }
@@ -123,11 +125,11 @@ __device__ __forceinline__ void warp_shaper_group(double* Lp, int& off, int& off
       cur[m] = nx1[m];
       nx1[m] = nx2[m];
     }
-    off = off1;
-    off1 = off2;
+    p0 = p1;
+    p1 = p2;
   }
   if constexpr (G + 1 < RM) {
-    if (k1 < d) warp_shaper_group<RM, G + 1>(Lp, off, off1, cur, nx1, scale, lane, d, xs, fr);
+    if (k1 < d) warp_shaper_group<RM, G + 1>(p0, p1, cur, nx1, scale, lane, d, xs, fr);
   }
 }
 
@@ -221,8 +223,8 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
 #pragma unroll
       for (int m = 0; m < RM; ++m) a[m] = 0.0;
       {
-        int off = 0;
-        warp_gemv_group<RM, 0>(Lg + lane, off, vec, s_n0, nscale, fresh, lane, d, a);
+        const double* pc = Lg + lane;
+        warp_gemv_group<RM, 0>(pc, vec, s_n0, nscale, fresh, lane, d, a);
       }
       __syncwarp(); /* z fully consumed: the vector takes the proposal */
 #pragma unroll
@@ -282,10 +284,11 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
         }
         {
           double cur[RM], nx1[RM];
-          int off = 0, off1 = d - 1;
-          warp_load_col<RM>(cur, Lg + lane, off, 0, lane, d);
-          warp_load_col<RM>(nx1, Lg + lane, off1, 1 < d ? 1 : 0x7fff, lane, d);
-          warp_shaper_group<RM, 0>(Lg + lane, off, off1, cur, nx1, scale, lane, d, xs, fr);
+          double* p0 = Lg + lane;    /* column k:     p0[32 m] = L(lane + 32 m, k) */
+          double* p1 = p0 + (d - 1); /* column k + 1 */
+          warp_load_col<RM>(cur, p0, 0, lane, d);
+          warp_load_col<RM>(nx1, p1, 1 < d ? 1 : 0x7fff, lane, d);
+          warp_shaper_group<RM, 0>(p0, p1, cur, nx1, scale, lane, d, xs, fr);
         }
         /* |L|_F: slot l = rows l, l+32, ... in order; halving tree over the 32 slots */
         double slot = 0.0;

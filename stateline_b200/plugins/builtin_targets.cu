@@ -73,22 +73,30 @@ struct GaussCorr {
     }
     return 0.5 * acc;
   }
+  /* columns c of row group G: only the row groups m <= G reach the diagonal, and only group G needs the row test */
+  template <int G>
+  __device__ __forceinline__ void dot_group(const double* x, u32 d, int lane, const double*& col, double* dot) const {
+    const u32 c1 = (32u * G + 32u < d) ? 32u * G + 32u : d;
+#pragma unroll 4
+    for (u32 c = 32u * G; c < c1; ++c) {
+      const double xc = x[c];
+#pragma unroll
+      for (int m = 0; m <= G; ++m)
+        if (m < G || (u32)lane + 32u * (u32)m <= c) dot[m] = fma(__ldg(col + 32 * m), xc, dot[m]);
+      col += d;
+    }
+    if constexpr (G < 3) {
+      if (c1 < d) dot_group<G + 1>(x, d, lane, col, dot);
+    }
+  }
   /* All job types with one warp (d <= 128).  Lane l owns rows l, l+32, ...: every row's dot product is still its own
    * fma chain over ascending c, the rows of a lane run interleaved, and U is read through its transpose (the second
    * matrix of the payload) so that the lanes of a row group read consecutive addresses.  Then lane j folds the rows
    * of job j in row order. */
   __device__ void warp_jobs(const double* x, u32 d, u32 n_jobs, int lane, double* values, double* dots) const {
-    const double* Ut = prm + 1 + (size_t)d * d; /* Ut[c * d + r] = U[r * d + c] */
+    const double* col = prm + 1 + (size_t)d * d + lane; /* Ut[c * d + r] = U[r * d + c], this lane's rows */
     double dot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (u32 c = 0; c < d; ++c) {
-      const double xc = x[c];
-      const double* col = Ut + (size_t)c * d;
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const u32 r = (u32)lane + 32u * (u32)m;
-        if (32u * (u32)m <= c && r <= c) dot[m] = fma(__ldg(col + r), xc, dot[m]); /* first test is warp-uniform */
-      }
-    }
+    dot_group<0>(x, d, lane, col, dot);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const u32 r = (u32)lane + 32u * (u32)m;
