@@ -854,7 +854,7 @@ def main():
             out["modes"] = {"welford": {
                 "value": S * T * K * R / (w_ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": w_ms / K,
                 "accept_rate_timed_region": [float(v) for v in w_acc],
-                "note": "gpu.shaper \"welford\": second-moment matrix updated per element on an accept, re-Cholesky at the adapt points; "
+                "note": "gpu.shaper \"welford\": accepted jumps are logged, folded into a second-moment matrix and re-factorised at the adapt points (rechol_kernel); "
                         "NOT the reference's arithmetic (no bit parity; tests/test_welford_gpu.py validates it statistically); the "
                         "headline above is the reference-exact mode"}}
         except Exception as ex:

@@ -79,10 +79,13 @@ const char* slgpu_version(void);
  *     byte-identical for both settings.  With overwrite every segment starts with a full set of rows.
  *   shaper "reference" (default) | "welford": NOT the reference's arithmetic.  "reference" is ProposalShaper::update
  *     (src/infer/adaptive.cpp:173-209: a rank-1 Cholesky update of the second moment of the accepted jumps on every accept)
- *     bit for bit.  "welford" keeps that second moment as a matrix, updates it element by element on an accept and
- *     re-factorises it at the adapt points (every adaptInterval rounds): the variant BASELINE's north star names, without
- *     the serial column sweep in the round; same adaptation in exact arithmetic, delayed by at most one launch.  Validated
- *     statistically only; nDims <= 32, dimensions the plugin lists in SLGPU_DEFINE_PLUGIN, batched schedule.
+ *     bit for bit.  "welford" keeps that second moment as a matrix: an accept only logs its jump vector, and at the adapt
+ *     points (every adaptInterval rounds) a second kernel folds the logged jumps into the matrix and re-factorises it: the
+ *     variant BASELINE's north star names, without the serial column sweep in the round; same adaptation in exact
+ *     arithmetic, delayed by at most adaptInterval rounds.  Validated statistically only; nDims <= 32, dimensions the
+ *     plugin lists in SLGPU_DEFINE_PLUGIN, batched schedule, adaptInterval <= 16 (the jump log has 16 slots per chain).
+ *     Measured on config #3 it is no faster than the default (step kernel 30 us per round instead of 47, re-Cholesky
+ *     23 us per round on top): DESIGN.md section 5.
  *   sink "bin": the delta stream appended to <outputPath>/chains-<stackOffset>.slgpu as it lands (stateline_b200/binlog.py
  *     reads it back into rows); the sink that keeps up with the GPU, csv is for small runs
  * plugin_path: likelihood plugin .so; plugin_entry: its table symbol (NULL = "slgpu_plugin_entry").

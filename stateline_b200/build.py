@@ -30,7 +30,7 @@ def nvcc():
 
 def _digest(deps, flags):
     """Content hash of the sources and flags: file times do not survive the copy to the GPU box."""
-    h = hashlib.sha256(" ".join(flags).encode())
+    h = hashlib.sha256(" ".join(flags).replace(ROOT, ".").encode())  # the checkout's own path is not part of the build
     for d in sorted(deps):
         h.update(os.path.basename(d).encode())
         with open(d, "rb") as f:

@@ -19,10 +19,12 @@ ap.add_argument("--shaper", default="reference", help="gpu.shaper: reference | w
 ap.add_argument("--plugin", default=None, help="path of a plugin .so built from the same targets (development: A/B builds)")
 ap.add_argument("--coarse", action="store_true", help="no per-launch events (lets programmatic dependent launch overlap)")
 a = ap.parse_args()
+if a.plugin:
+    os.environ["SLGPU_TARGETS_SO"] = os.path.abspath(a.plugin)  # the built-in entry names, looked up in this build
 w = configs.workload(a.workload, S=a.stacks)
 if a.swap:
     w["swapInterval"] = a.swap
-with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLaunch=a.mrl, shaper=a.shaper), plugin=a.plugin or w["plugin"], payload=w["payload"]) as e:
+with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLaunch=a.mrl, shaper=a.shaper), plugin=w["plugin"], payload=w["payload"]) as e:
     e.init_chains()
     e.step_rounds(a.warm)
     e.sync()
