@@ -58,24 +58,49 @@ __device__ __forceinline__ void warp_load_col(double* dst, const double* pc, int
 }
 
 /* proposal GEMV, columns of row group G: a_j = fma(N_jk, z_k, a_j), k ascending.  pc walks the columns (pc = Lp + off_k):
- * the loads of a column are pc[32 m] with immediate offsets */
+ * the loads of a column are pc[32 m] with immediate offsets.  Columns go in batches of B: all loads of a batch are issued
+ * before its first fma (a loop the compiler unrolls keeps one column in flight: its exits sit between the columns), with
+ * B sized so that a batch is at most eight loads per lane. */
+template <int RM, int G>
+__device__ __forceinline__ void warp_gemv_column(const double* pc, int k, const double* vec, const double* s_n0, double nscale, bool fresh,
+                                                 int lane, int d, const double* v, double* a) {
+  const double zk = vec[k];
+  const double n0k = s_n0[k];
+#pragma unroll
+  for (int m = G; m < RM; ++m) {
+    const int j = lane + 32 * m;
+    if ((m > G || j >= k) && j < d) {
+      double njk = (v ? v[m - G] : pc[32 * m]) * nscale;
+      if (m == G && j == k) njk = fresh ? n0k : njk + 1e-4;
+      a[m] = fma(njk, zk, a[m]);
+    }
+  }
+}
 template <int RM, int G>
 __device__ __forceinline__ void warp_gemv_group(const double*& pc, const double* vec, const double* s_n0, double nscale, bool fresh,
                                                 int lane, int d, double* a) {
+  constexpr int NG = RM - G;
+  constexpr int B = NG >= 3 ? 2 : (NG == 2 ? 4 : 8);
   const int k1 = (32 * G + 32 < d) ? 32 * G + 32 : d;
-#pragma unroll kWarpGemvUnroll
-  for (int k = 32 * G; k < k1; ++k) {
-    const double zk = vec[k];
-    const double n0k = s_n0[k];
+  int k = 32 * G;
+  for (; k + B <= k1; k += B) {
+    double v[B][NG];
+    const double* q = pc;
 #pragma unroll
-    for (int m = G; m < RM; ++m) {
-      const int j = lane + 32 * m;
-      if ((m > G || j >= k) && j < d) {
-        double njk = pc[32 * m] * nscale;
-        if (m == G && j == k) njk = fresh ? n0k : njk + 1e-4;
-        a[m] = fma(njk, zk, a[m]);
+    for (int b = 0; b < B; ++b) {
+#pragma unroll
+      for (int m = G; m < RM; ++m) {
+        const int j = lane + 32 * m;
+        v[b][m - G] = ((m > G || j >= k + b) && j < d) ? q[32 * m] : 0.0;
       }
+      q += d - (k + b) - 1;
     }
+#pragma unroll
+    for (int b = 0; b < B; ++b) warp_gemv_column<RM, G>(nullptr, k + b, vec, s_n0, nscale, fresh, lane, d, v[b], a);
+    pc = q;
+  }
+  for (; k < k1; ++k) {
+    warp_gemv_column<RM, G>(pc, k, vec, s_n0, nscale, fresh, lane, d, nullptr, a);
     pc += d - k - 1;
   }
   if constexpr (G + 1 < RM) {
@@ -132,6 +157,18 @@ __device__ __forceinline__ void warp_shaper_group(double*& p0, double*& p1, doub
     if (k1 < d) warp_shaper_group<RM, G + 1>(p0, p1, cur, nx1, scale, lane, d, xs, fr);
   }
 }
+
+#ifdef SLGPU_WSTAMPS /* development: clock stamps of round SLGPU_WSTAMPS for every 16th chain, 16 x i64 into the round_flags buffer */
+#define SLGPU_WSTAMP(k)                                                                     \
+  do {                                                                                      \
+    if (lane == 0 && active && p.round_flags && it == (SLGPU_WSTAMPS) && (c & 15u) == 0u)   \
+      ((long long*)p.round_flags)[(size_t)c + (k)] = clock64();                             \
+  } while (0)
+#else
+#define SLGPU_WSTAMP(k) \
+  do {                  \
+  } while (0)
+#endif
 
 template <class Lik, int RM, int MAXT>
 __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp_kernel(const slgpu_step_params p) {
@@ -197,7 +234,11 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
   for (u32 it = 0; it < p.n_rounds; ++it) {
     const u64 r = p.round_begin + it;
     bool acc = false;
+    SLGPU_WSTAMP(0);
     if (active) {
+#ifdef SLGPU_WARP_L2_PREFETCH
+      for (int e = 16 * lane; e < (int)nL; e += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(Lg + e));
+#endif
       /* ---- normals: lane l makes the Box-Muller pairs l, l+32, ... ---- */
       const double* zr = replay ? p.rp_z + ((size_t)r * C + c) * d : nullptr;
       for (int kp = lane; kp < (d + 1) / 2; kp += 32) {
@@ -217,6 +258,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
         if (2 * kp + 1 < d) vec[2 * kp + 1] = z1;
       }
       __syncwarp();
+      SLGPU_WSTAMP(1);
       /* ---- proposal: a_j = sum_{k<=j} fma(N_jk, z_k, .), k ascending; one coalesced column segment per row group ---- */
       const bool fresh = (sh_count == p.sh_count0);
       double a[RM];
@@ -227,6 +269,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
         warp_gemv_group<RM, 0>(pc, vec, s_n0, nscale, fresh, lane, d, a);
       }
       __syncwarp(); /* z fully consumed: the vector takes the proposal */
+      SLGPU_WSTAMP(2);
 #pragma unroll
       for (int m = 0; m < RM; ++m) {
         const int j = lane + 32 * m;
@@ -245,6 +288,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       }
       double e_new = 0.0;
       for (int jj = 0; jj < J; ++jj) e_new += fv[jj];
+      SLGPU_WSTAMP(3);
       /* ---- acceptProposal (chainarray.cpp:30-45), append (:94-121) ---- */
       if (!isinf(e_new)) {
         double u;
@@ -270,6 +314,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       stats_accumulate<1>(Ps, -8.0, 4.0, slm_log(row_sigma), logtemper, acc);
       sigma = slm_exp(predict(w3, p.opt_accept, -8.0, 4.0, logtemper));
       /* ---- ProposalShaper::update (adaptive.cpp:173-209), in place: accept is warp-uniform ---- */
+      SLGPU_WSTAMP(4);
       if (acc) {
         const double eps = 1e-18;
         sh_count += 1.0;
@@ -305,6 +350,7 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       }
     }
 
+    SLGPU_WSTAMP(5);
     /* ================= swap sweep of the stack, through shared memory ================= */
     double mid_e = energy;
     int mid_acc = accepted;
@@ -364,12 +410,17 @@ __global__ void __launch_bounds__(MAXT, SLGPU_WARP_MINBLOCKS(MAXT)) pt_step_warp
       __syncthreads(); /* the scratch is reused next swap round */
     }
 
+    SLGPU_WSTAMP(6);
     if (active) {
       lg_min_e = smin(lg_min_e, mid_e);
       lg_accepts += (u32)mid_acc;
       lg_swaps += (swap_type == 1);
       lg_att += (swap_type != 0);
+#ifndef SLGPU_WSTAMPS
       if (p.round_flags) p.round_flags[(size_t)it * C + c] = (unsigned char)((acc ? 1 : 0) | (swap_type << 1));
+#else
+      if (lane == 0 && p.round_flags && it == (SLGPU_WSTAMPS) && (c & 15u) == 0u) ((long long*)p.round_flags)[(size_t)c + 7] = acc ? 1 : 0;
+#endif
       if (it + 1 == p.n_rounds) p.lg_cur_energy[c] = mid_e; /* TableLogger energies_ (logging.cpp:43) */
       if (t == 0) {
         const double nn = (double)(r + 1);

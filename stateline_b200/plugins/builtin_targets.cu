@@ -73,12 +73,30 @@ struct GaussCorr {
     }
     return 0.5 * acc;
   }
-  /* columns c of row group G: only the row groups m <= G reach the diagonal, and only group G needs the row test */
+  /* columns c of row group G: only the row groups m <= G reach the diagonal, and only group G needs the row test.  The
+   * columns go in batches whose loads are all issued before the first fma (at most eight per lane). */
   template <int G>
   __device__ __forceinline__ void dot_group(const double* x, u32 d, int lane, const double*& col, double* dot) const {
+    constexpr int NG = G + 1;
+    constexpr int B = NG >= 3 ? 2 : (NG == 2 ? 4 : 8);
     const u32 c1 = (32u * G + 32u < d) ? 32u * G + 32u : d;
-#pragma unroll 4
-    for (u32 c = 32u * G; c < c1; ++c) {
+    u32 c = 32u * G;
+    for (; c + B <= c1; c += B) {
+      double v[B][NG];
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int m = 0; m <= G; ++m) v[b][m] = (m < G || (u32)lane + 32u * (u32)m <= c + b) ? __ldg(col + (size_t)b * d + 32 * m) : 0.0;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const double xc = x[c + b];
+#pragma unroll
+        for (int m = 0; m <= G; ++m)
+          if (m < G || (u32)lane + 32u * (u32)m <= c + b) dot[m] = fma(v[b][m], xc, dot[m]);
+      }
+      col += (size_t)B * d;
+    }
+    for (; c < c1; ++c) {
       const double xc = x[c];
 #pragma unroll
       for (int m = 0; m <= G; ++m)
