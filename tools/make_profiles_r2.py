@@ -101,4 +101,10 @@ for c, pat in ((4, 'pt_step_warp_kernel.*GaussCorr.*Li4E'), (5, 'pt_step_warp_ke
     md += ['', 'DRAM traffic per launch: %.3g B' % tr[0], '', '### per source line', '', '```'] + per_line('r2_w%d' % c, pat, 14).split('\n') + ['```', '']
 os.remove(os.path.join(P, '_tmp.md'))
 open(os.path.join(P, 'r2_warp_kernel_ncu.md'), 'w').write('\n'.join(md) + '\n')
+
+# ---- the re-Cholesky kernel of the opt-in welford mode ----
+if os.path.exists(os.path.join(G, 'r2_rechol_raw.csv')):
+    out, tr = metrics('r2_rechol', 'r2_rechol_ncu_metrics.md', 'rechol_kernel<20> ("gpu": {"shaper": "welford"}), config #3, one adapt point',
+                      'ncu --set full --clock-control none --import-source on -k regex:rechol -s 3 -c 1 … python tools/probe.py --workload config3 --warm 60 --rounds 30 --shaper welford')
+    print('rechol traffic', tr)
 print('done')
