@@ -84,8 +84,8 @@ const char* slgpu_version(void);
  *     variant BASELINE's north star names, without the serial column sweep in the round; same adaptation in exact
  *     arithmetic, delayed by at most adaptInterval rounds.  Validated statistically only; nDims <= 32, dimensions the
  *     plugin lists in SLGPU_DEFINE_PLUGIN, batched schedule, adaptInterval <= 16 (the jump log has 16 slots per chain).
- *     Measured on config #3 it is no faster than the default (step kernel 30 us per round instead of 47, re-Cholesky
- *     23 us per round on top): DESIGN.md section 5.
+ *     Measured on config #3: step kernel 30 us per round instead of 47, the re-Cholesky 17 us per round on top: 4 %
+ *     faster than the default in steady state, 9-10 % while the hot tiers still accept everything.
  *   sink "bin": the delta stream appended to <outputPath>/chains-<stackOffset>.slgpu as it lands (stateline_b200/binlog.py
  *     reads it back into rows); the sink that keeps up with the GPU, csv is for small runs
  * plugin_path: likelihood plugin .so; plugin_entry: its table symbol (NULL = "slgpu_plugin_entry").

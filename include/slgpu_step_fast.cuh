@@ -637,12 +637,130 @@ __global__ void __launch_bounds__(NT, SLGPU_FAST_MINBLOCKS) pt_step_fast_kernel(
 #define SLGPU_RECHOL_WARPS 4
 #endif
 constexpr int kRecholWarps = SLGPU_RECHOL_WARPS;
+
+/* the work of warp W of a rechol block: its rows j = W, W + NW, ... of the 32 matrices of the tile live in REGISTERS from the
+ * fold to the write-back (every index below is a compile-time constant once W is), the tile in shared memory carries what
+ * the warps exchange: the original diagonal, and the finished entries of L, which the other warps read as row k */
+template <int D, int NW, int W>
+__device__ __forceinline__ void rechol_rows(const slgpu_step_params& p, double* s_t, double* s_j, double* s_fr, unsigned long long* s_bar,
+                                            int lane, u32 c, size_t C, bool active, int n_logged, int n_max, double* Cg, double* Lg) {
+  constexpr int RPT = (D - W + NW - 1) / NW; /* rows of this warp */
+  double R[RPT > 0 ? RPT : 1][D];            /* R[r][k], k <= j_r = W + r NW */
+  double* A = s_t + lane;                    /* this chain's matrix in the tile: A[idx * 32] */
+  const double cnt = active ? p.sh_count[c] : 1.0;
+  double nxt[RPT > 0 ? RPT : 1]; /* this warp's rows of the NEXT logged jump, in flight while the current one is folded */
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) nxt[r] = (0 < n_logged) ? __ldcs(p.jump_log + (size_t)(W + r * NW) * C + c) : 0.0;
+  for (int q = 0; q < n_max; ++q) {
+    if (q) __syncthreads(); /* the previous jump has been consumed */
+    const bool has = q < n_logged;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      s_j[(W + r * NW) * 32 + lane] = nxt[r];
+      nxt[r] = (q + 1 < n_logged) ? __ldcs(p.jump_log + ((size_t)(q + 1) * D + (W + r * NW)) * C + c) : 0.0;
+    }
+    __syncthreads();
+    if (q == 0) {
+      mbar_wait(s_bar, 0); /* the tile is here: take the rows */
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int j = W + r * NW;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+          if (k <= j) R[r][k] = A[(j * (j + 1) / 2 + k) * 32];
+      }
+    }
+    if (has) {
+      const double n = cnt - (double)(n_logged - 1 - q);
+      const double fold = (n - 1.0) / n, rn = 1.0 / n;
+      double sjn[RPT > 0 ? RPT : 1];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) sjn[r] = s_j[(W + r * NW) * 32 + lane] * rn;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (k <= W + (RPT - 1) * NW) { /* some row of this warp reaches column k */
+          const double sk = s_j[k * 32 + lane];
+#pragma unroll
+          for (int r = 0; r < RPT; ++r)
+            if (k <= W + r * NW) R[r][k] = fma(sjn[r], sk, R[r][k] * fold);
+        }
+      }
+    }
+  }
+  const bool redo = n_logged > 0;
+  /* the moment matrix itself goes back before it is factorised; the diagonal also to the tile (the other warps' pivots) */
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int j = W + r * NW;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+      if (k <= j) {
+        if (redo) Cg[(size_t)(j * (j + 1) / 2 + k) * 32 + lane] = R[r][k];
+        if (k == j) A[(j * (j + 1) / 2 + k) * 32] = R[r][k];
+      }
+  }
+  __syncthreads();
+  double frob = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    constexpr int dummy2 = 0;
+    (void)dummy2;
+    const int rk = k * (k + 1) / 2;
+    double acc[RPT > 0 ? RPT : 1];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = (W + r * NW > k) ? R[r][k] : 0.0;
+    double piv = A[(rk + k) * 32]; /* C[k][k] */
+#pragma unroll
+    for (int m = 0; m < k; ++m) {
+      const double akm = A[(rk + m) * 32]; /* L[k][m], finished in column m */
+      piv = fma(-akm, akm, piv);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+        if (W + r * NW > k) acc[r] = fma(-R[r][m], akm, acc[r]);
+    }
+    const double lkk = sqrt(smax(piv, 1e-300));
+    const double rl = 1.0 / lkk;
+    if (k % NW == W) {
+      R[(k - W) / NW < RPT ? (k - W) / NW : 0][k] = lkk; /* (the guard only keeps the index in range for other W) */
+      frob = fma(lkk, lkk, frob);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+      if (W + r * NW > k) {
+        const double w = acc[r] * rl;
+        R[r][k] = w;
+        A[((W + r * NW) * (W + r * NW + 1) / 2 + k) * 32] = w; /* row j is read by everybody when it becomes the pivot row */
+        frob = fma(w, w, frob);
+      }
+    __syncthreads();
+  }
+  s_fr[W * 32 + lane] = frob;
+  if (redo) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int j = W + r * NW;
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+        if (k <= j) Lg[(size_t)(j * (j + 1) / 2 + k) * 32 + lane] = R[r][k];
+    }
+  }
+  __syncthreads();
+  if (W == 0 && redo) {
+    double f = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) f += s_fr[w * 32 + lane];
+    p.nscale[c] = p.prop_norm / smax(sqrt(f), 1e-18);
+    p.chol_dirty[c] = 0;
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kRecholWarps * 32) rechol_kernel(const slgpu_step_params p) {
   constexpr int NL = D * (D + 1) / 2;
   constexpr int NW = kRecholWarps;
-  constexpr int RPT = (D + NW - 1) / NW; /* rows per thread */
-  extern __shared__ double s_t[];        /* [NL][32] the tile, [D][32] the jump being folded (then the new diagonal), [NW][32] partial norms */
+  extern __shared__ double s_t[]; /* [NL][32] the tile, [D][32] the jump being folded, [NW][32] partial norms */
   double* s_j = s_t + NL * 32;
   double* s_fr = s_j + D * 32;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -662,103 +780,16 @@ __global__ void __launch_bounds__(kRecholWarps * 32) rechol_kernel(const slgpu_s
     mbar_expect_tx(&s_bar, NL * 32 * (unsigned)sizeof(double));
     bulk_load(s_t, Cg, NL * 32 * (unsigned)sizeof(double), &s_bar); /* the whole tile in one bulk copy */
   }
-  double* A = s_t + lane; /* this chain's matrix: A[idx * 32] */
-  const double cnt = active ? p.sh_count[c] : 1.0;
-  double nxt[RPT]; /* the rows this warp stages of the NEXT logged jump: its load is in flight while the current one is folded */
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int i = wid + r * NW;
-    nxt[r] = (i < D && 0 < n_logged) ? __ldcs(p.jump_log + (size_t)i * C + c) : 0.0;
-  }
-  for (int q = 0; q < n_max; ++q) {
-    if (q) __syncthreads(); /* the previous jump has been consumed */
-    const bool has = q < n_logged;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int i = wid + r * NW;
-      if (i < D) s_j[i * 32 + lane] = nxt[r];
-      nxt[r] = (i < D && q + 1 < n_logged) ? __ldcs(p.jump_log + ((size_t)(q + 1) * D + i) * C + c) : 0.0;
-    }
-    __syncthreads();
-    if (q == 0) mbar_wait(&s_bar, 0);
-    if (has) {
-      const double n = cnt - (double)(n_logged - 1 - q);
-      const double fold = (n - 1.0) / n, rn = 1.0 / n;
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int j = wid + r * NW;
-        if (j < D) {
-          const double sjn = s_j[j * 32 + lane] * rn;
-          double* e = A + (j * (j + 1) / 2) * 32;
-          int k = 0;
-          for (; k + 4 <= j + 1; k += 4) { /* four independent elements at a time */
-            const double e0 = e[k * 32], e1 = e[(k + 1) * 32], e2 = e[(k + 2) * 32], e3 = e[(k + 3) * 32];
-            const double s0 = s_j[k * 32 + lane], s1 = s_j[(k + 1) * 32 + lane], s2 = s_j[(k + 2) * 32 + lane], s3 = s_j[(k + 3) * 32 + lane];
-            e[k * 32] = fma(sjn, s0, e0 * fold);
-            e[(k + 1) * 32] = fma(sjn, s1, e1 * fold);
-            e[(k + 2) * 32] = fma(sjn, s2, e2 * fold);
-            e[(k + 3) * 32] = fma(sjn, s3, e3 * fold);
-          }
-          for (; k <= j; ++k) e[k * 32] = fma(sjn, s_j[k * 32 + lane], e[k * 32] * fold);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const bool redo = n_logged > 0;
-  if (redo)
-    for (int i = wid; i < NL; i += NW) Cg[(size_t)i * 32 + lane] = A[i * 32]; /* the moment matrix itself, before it is factorised in place */
-  __syncthreads();
-  double frob = 0.0;
-  for (int k = 0; k < D; ++k) {
-    const int rk = k * (k + 1) / 2;
-    /* the rows of this thread below the diagonal of column k: their dot products with row k advance together, and so does
-     * row k's own (the pivot), which every thread carries for itself */
-    double acc[RPT];
-    int rowoff[RPT];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      int j = wid + r * NW;
-      if (j >= D || j <= k) j = k; /* a spare slot repeats row k: valid addresses, its result is not used */
-      rowoff[r] = (j * (j + 1) / 2) * 32;
-      acc[r] = A[rowoff[r] + k * 32];
-    }
-    double piv = A[(rk + k) * 32];
-    for (int m = 0; m < k; ++m) {
-      const double akm = A[(rk + m) * 32];
-      piv = fma(-akm, akm, piv);
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) acc[r] = fma(-A[rowoff[r] + m * 32], akm, acc[r]);
-    }
-    const double lkk = sqrt(smax(piv, 1e-300));
-    const double rl = 1.0 / lkk;
-    if ((k % NW) == wid) {
-      s_j[k * 32 + lane] = lkk; /* parked beside the tile: the other warps may still be reading C[k][k] */
-      frob = fma(lkk, lkk, frob);
-    }
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int j = wid + r * NW;
-      if (j > k && j < D) {
-        const double w = acc[r] * rl;
-        A[rowoff[r] + k * 32] = w;
-        frob = fma(w, w, frob);
-      }
-    }
-    __syncthreads();
-  }
-  s_fr[wid * 32 + lane] = frob;
-  for (int k = wid; k < D; k += NW) A[(k * (k + 1) / 2 + k) * 32] = s_j[k * 32 + lane];
-  __syncthreads();
-  if (redo) {
-    for (int i = wid; i < NL; i += NW) Lg[(size_t)i * 32 + lane] = A[i * 32];
-    if (wid == 0) {
-      double f = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) f += s_fr[w * 32 + lane];
-      p.nscale[c] = p.prop_norm / smax(sqrt(f), 1e-18);
-      p.chol_dirty[c] = 0;
-    }
+  static_assert(NW == 4 || NW == 2 || NW == 8, "rechol_rows is instantiated per warp below");
+  switch (wid) { /* warp-uniform: every index inside is static */
+    case 0: rechol_rows<D, NW, 0>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 1: rechol_rows<D, NW, 1>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 2: if constexpr (NW > 2) rechol_rows<D, NW, 2>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 3: if constexpr (NW > 2) rechol_rows<D, NW, 3>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 4: if constexpr (NW > 4) rechol_rows<D, NW, 4>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 5: if constexpr (NW > 4) rechol_rows<D, NW, 5>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    case 6: if constexpr (NW > 4) rechol_rows<D, NW, 6>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
+    default: if constexpr (NW > 4) rechol_rows<D, NW, 7>(p, s_t, s_j, s_fr, &s_bar, lane, c, C, active, n_logged, n_max, Cg, Lg); break;
   }
 }
 

@@ -66,6 +66,11 @@ def _headers():
     return hs
 
 
+def _plugin_headers():
+    """What a likelihood plugin compiles: the device headers (slgpu.h is the host API and no part of a plugin build)."""
+    return [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE) if f != "slgpu.h"]
+
+
 def build_engine(force=False, verbose=False):
     src = os.path.join(CSRC, "engine.cu")
     flags = ARCH + COMMON + ["-O2", "-ldl"]
@@ -80,7 +85,7 @@ def build_engine(force=False, verbose=False):
 def build_plugin(src, out, force=False, verbose=False, extra=()):
     """Compile a likelihood plugin translation unit (it includes slgpu_device.cuh) into a .so."""
     flags = ARCH + COMMON + ["-O3"] + list(extra)
-    digest = _digest([src] + _headers(), flags)
+    digest = _digest([src] + _plugin_headers(), flags)
     if force and os.path.exists(out + ".srchash"):
         os.remove(out + ".srchash")
     if _stale(out, digest):
