@@ -13,6 +13,7 @@
 // device segment buffers; with sink "host"/"csv" a second stream copies each finished segment into a
 // pinned host ring while the next launch runs.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
 #include <dlfcn.h>
 #include <sys/stat.h>
 
@@ -37,6 +38,14 @@
 #include "slgpu_plugin.h"
 #include "row_compact.cuh"
 #include "tier_kernels.cuh"
+
+// NVTX ranges on the host-side phases of the step loop (nsys / ncu --nvtx timelines)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 namespace {
 
@@ -578,6 +587,7 @@ void csv_pool_stop(slgpu_engine* e) {
 // format every landed row into the per-stack buffers (one <outputPath>/<stack>.csv per stack, db.cpp:27-35);
 // buffers go to the files when they hold 64 MiB together, and at the end (finalise)
 slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
+  NvtxRange nvtx_("slgpu:csv_pump");
   poll_landed(e, block);
   {
     slgpu_status st = materialise(e);
@@ -609,6 +619,7 @@ slgpu_status csv_pump(slgpu_engine* e, bool block, bool finalise) {
 // flags, payload[count]).  stateline_b200/binlog.py rebuilds the rows.  This is the sink that keeps up with the GPU:
 // ~50 bytes per cold row instead of ~150 characters of text.
 slgpu_status bin_pump(slgpu_engine* e, bool block, bool finalise) {
+  NvtxRange nvtx_("slgpu:bin_pump");
   poll_landed(e, block);
   while (!e->hsegs.empty() && e->hsegs.front().landed) {
     const HostSeg& hs = e->hsegs.front();
@@ -684,6 +695,7 @@ bool cring_reserve(slgpu_engine* e, size_t bytes, size_t* off) {
 // rest in the rare case that was short.  A compact device buffer is reused only after the host has seen its segment
 // land, so that such a late fetch always finds its data.
 slgpu_status enqueue_compact(slgpu_engine* e, const double* rows_dev, uint32_t n_rounds) {
+  NvtxRange nvtx_("slgpu:compact_rows");
   const uint32_t S = e->cfg.nStacks, d = e->cfg.nDims;
   CompactBuf& cb = e->cbuf[e->seg_next % kCompactBufs];
   for (HostSeg& hs : e->hsegs) {  // the segment that used this buffer last, if it is still in flight
@@ -742,6 +754,7 @@ slgpu_status enqueue_compact(slgpu_engine* e, const double* rows_dev, uint32_t n
 
 // one launch of the plugin's step kernel over [rounds_done, rounds_done + n)
 slgpu_status launch_rounds(slgpu_engine* e, uint32_t n) {
+  NvtxRange nvtx_("slgpu:launch_rounds");
   const bool emit = e->cfg.sink != SINK_NONE;
   const bool to_host = e->cfg.sink == SINK_HOST || e->cfg.sink == SINK_CSV || e->cfg.sink == SINK_BIN;
   const uint64_t n_rows = (uint64_t)n * e->cfg.nStacks;
@@ -831,6 +844,7 @@ slgpu_status sequential_scan(slgpu_engine* e) {
 }
 
 slgpu_status adapt_point(slgpu_engine* e) {
+  NvtxRange nvtx_("slgpu:adapt_point");
   const uint32_t T = e->cfg.nTemps;
   slgpu_tier::k_tier_adapt<<<dim3(T, 2, 9), 256, 0, e->compute>>>(e->P.p_sig, e->P.p_beta, e->cfg.nStacks, T, e->d_sums, e->d_ticket, e->d_models,
                                                                   e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
@@ -1228,6 +1242,7 @@ slgpu_status slgpu_init_chains(slgpu_engine* e) {
 }
 
 slgpu_status slgpu_step_rounds(slgpu_engine* e, uint64_t n_rounds) {
+  NvtxRange nvtx_("slgpu:step_rounds");
   slgpu_status st = check_ready(e, true);
   if (st != SLGPU_OK) return st;
   if (e->cfg.rng == SLGPU_RNG_REPLAY && e->rounds_done + n_rounds > e->P.replay_rounds)
@@ -1314,6 +1329,7 @@ uint32_t slgpu_n_dims(const slgpu_engine* e) { return e ? e->cfg.nDims : 0; }
 uint32_t slgpu_n_chains(const slgpu_engine* e) { return e ? (uint32_t)e->C : 0; }
 
 slgpu_status slgpu_drain(slgpu_engine* e, double* rows, size_t cap_rows, size_t* n_rows) {
+  NvtxRange nvtx_("slgpu:drain");
   slgpu_status st = check_ready(e, false);
   if (st != SLGPU_OK) return st;
   if (!n_rows || (!rows && cap_rows)) return fail(SLGPU_E_ARG, "rows / n_rows must not be NULL");
@@ -1832,6 +1848,7 @@ struct FileCloser {
 }  // namespace
 
 slgpu_status slgpu_save_state(slgpu_engine* e, const char* path) {
+  NvtxRange nvtx_("slgpu:save_state");
   slgpu_status st = check_ready(e, true);
   if (st != SLGPU_OK) return st;
   if (!path || !path[0]) return fail(SLGPU_E_ARG, "path must not be empty");
@@ -1863,6 +1880,7 @@ slgpu_status slgpu_save_state(slgpu_engine* e, const char* path) {
 }
 
 slgpu_status slgpu_load_state(slgpu_engine* e, const char* path) {
+  NvtxRange nvtx_("slgpu:load_state");
   slgpu_status st = check_ready(e, false);
   if (st != SLGPU_OK) return st;
   if (!path || !path[0]) return fail(SLGPU_E_ARG, "path must not be empty");
