@@ -845,18 +845,20 @@ def main():
     if not args.no_side and world == 1:
         # the opt-in non-reference shaper (north star's "Welford + periodic re-Cholesky"): same workload, same timer, for context
         try:
-            cfg_w = configs.engine_config(w, sink="device", device=local_rank, seed=1234, shaper="welford")
-            with Engine(cfg_w, plugin=w["plugin"], payload=w["payload"]) as e:
-                e.init_chains()
-                e.step_rounds(W * R - 1)
-                e.sync()
-                w_ms, _, _, w_acc, _ = timed_steps(e, K, R, per_launch=False)
-            out["modes"] = {"welford": {
-                "value": S * T * K * R / (w_ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": w_ms / K,
-                "accept_rate_timed_region": [float(v) for v in w_acc],
-                "note": "gpu.shaper \"welford\": accepted jumps are logged, folded into a second-moment matrix and re-factorised at the adapt points (rechol_kernel); "
-                        "NOT the reference's arithmetic (no bit parity; tests/test_welford_gpu.py validates it statistically); the "
-                        "headline above is the reference-exact mode"}}
+            out["modes"] = {}
+            for key, every in (("welford", 1), ("welford_rechol_every_3", 3)):
+                cfg_w = configs.engine_config(w, sink="device", device=local_rank, seed=1234, shaper="welford", recholEvery=every)
+                with Engine(cfg_w, plugin=w["plugin"], payload=w["payload"]) as e:
+                    e.init_chains()
+                    e.step_rounds(W * R - 1)
+                    e.sync()
+                    w_ms, _, _, w_acc, _ = timed_steps(e, K, R, per_launch=False)
+                out["modes"][key] = {
+                    "value": S * T * K * R / (w_ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": w_ms / K, "rechol_every_adapt_points": every,
+                    "accept_rate_timed_region": [float(v) for v in w_acc],
+                    "note": "gpu.shaper \"welford\": accepted jumps are logged, folded into a second-moment matrix and re-factorised at every "
+                            "n-th adapt point (rechol_kernel); NOT the reference's arithmetic (no bit parity; tests/test_welford_gpu.py "
+                            "validates it statistically); the headline above is the reference-exact mode"}
         except Exception as ex:
             sys.stderr.write("welford mode arm failed (%r)\n" % (ex,))
     if not args.no_ess:

@@ -83,7 +83,8 @@ const char* slgpu_version(void);
  *     points (every adaptInterval rounds) a second kernel folds the logged jumps into the matrix and re-factorises it: the
  *     variant BASELINE's north star names, without the serial column sweep in the round; same adaptation in exact
  *     arithmetic, delayed by at most adaptInterval rounds.  Validated statistically only; nDims <= 32, dimensions the
- *     plugin lists in SLGPU_DEFINE_PLUGIN, batched schedule, adaptInterval <= 16 (the jump log has 16 slots per chain).
+ *     plugin lists in SLGPU_DEFINE_PLUGIN, batched schedule.  recholEvery (default 1): re-factorise at every n-th adapt
+ *     point only; adaptInterval * recholEvery <= 32 (the slots of the jump log per chain).
  *     Measured on config #3: step kernel 30 us per round instead of 47, the re-Cholesky 17 us per round on top: 4 %
  *     faster than the default in steady state, 9-10 % while the hot tiers still accept everything.
  *   sink "bin": the delta stream appended to <outputPath>/chains-<stackOffset>.slgpu as it lands (stateline_b200/binlog.py

@@ -37,7 +37,7 @@ extern "C" {
   (SLGPU_L_LAYOUT(n_dims) == SLGPU_L_COLMAJOR                                                                           \
        ? (((size_t)(n_stacks) * (n_temps) + 127u) / 128u * 128u) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u)           \
        : (size_t)(((n_stacks) + 32u / (n_temps) - 1u) / (32u / (n_temps))) * ((size_t)(n_dims) * ((n_dims) + 1u) / 2u) * SLGPU_L_TILE)
-#define SLGPU_JUMP_LOG_SLOTS 16u /* "gpu": {"shaper": "welford"}: accepted jumps a chain can log between two adapt points */
+#define SLGPU_JUMP_LOG_SLOTS 32u /* "gpu": {"shaper": "welford"}: accepted jumps a chain can log between two re-Cholesky passes */
 #define SLGPU_ROW_EXTRA 5u   /* energy, sigma, beta, accepted, swapType (src/db/db.cpp:18-25) */
 
 enum { SLGPU_RNG_REPLAY = 0, SLGPU_RNG_PHILOX = 1 };
@@ -110,8 +110,8 @@ typedef struct slgpu_step_params {
   const void* payload;     /* the plugin's POD payload, copied to the device by the engine */
   /* "gpu": {"shaper": "welford"} -- NOT the reference's arithmetic, off by default (moment == NULL): the second moment of the
    * accepted jumps is kept as a matrix, moment[] in the layout of L.  An accept only appends its jump vector to the chain's
-   * log, jump_log[(slot * d + i) * C + chain] with slot = chol_dirty[chain]++ (at most SLGPU_JUMP_LOG_SLOTS between two adapt
-   * points); launch_rechol, at the adapt points, folds the logged jumps into the matrix (C <- (n-1)/n C + s s^T / n, the
+   * log, jump_log[(slot * d + i) * C + chain] with slot = chol_dirty[chain]++ (at most SLGPU_JUMP_LOG_SLOTS between two calls of
+   * launch_rechol); launch_rechol, at every recholEvery-th adapt point, folds the logged jumps into the matrix (C <- (n-1)/n C + s s^T / n, the
    * recurrence L L^T follows in adaptive.cpp:173-197) and re-factorises L from it. */
   double* moment;
   double* jump_log;

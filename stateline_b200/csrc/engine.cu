@@ -92,6 +92,7 @@ struct Settings {
   bool windowRates = false;  // keep the adapters' windowed accept / swap rates (the AcptRt / SwapRt columns of the table logger)
   uint32_t csvThreads = 0;  // csv sink: formatter threads (0 = one per host core, at most 16)
   bool append = false;  // csv sink: keep existing <stack>.csv files (a resumed run) instead of truncating them
+  uint32_t recholEvery = 1;  // "shaper": "welford": adapt points between two re-Cholesky passes
   bool welford = false;  // "shaper": "welford": second-moment matrix + periodic re-Cholesky (NOT the reference's update; opt-in)
 };
 
@@ -308,6 +309,7 @@ Settings parse_settings(const char* text) {
       else if (k == "welford") s.welford = true;
       else throw ConfigError{"gpu.shaper must be \"reference\" or \"welford\""};
     }
+    if (g->find("recholEvery")) s.recholEvery = (uint32_t)need_uint(*g, "recholEvery");
     if (g->find("wire")) {
       const std::string& k = need(*g, "wire", slgpu_json::Value::String).str;
       if (k == "delta") s.wire = WIRE_DELTA;
@@ -850,7 +852,8 @@ slgpu_status adapt_point(slgpu_engine* e) {
                                                                   e->d_sig_w, e->cfg.optimalSwapRate, e->d_ladder);
   CU_TRY(cudaGetLastError());
   e->launches += 1;
-  if (e->cfg.welford) {  // the periodic re-Cholesky: at the adapt points (a schedule in rounds, not in launches), for the chains an accept has marked
+  // the periodic re-Cholesky: at every recholEvery-th adapt point (a schedule in rounds, not in launches), for the chains that logged a jump
+  if (e->cfg.welford && ((e->rounds_done + 1) / e->cfg.adaptInterval) % e->cfg.recholEvery == 0) {
     const int rc2 = e->plug->launch_rechol ? e->plug->launch_rechol(&e->P, (void*)e->compute) : (int)cudaErrorNotSupported;
     if (rc2 != 0) {
       e->failed = true;
@@ -995,9 +998,9 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
     TRY_ST(dev_alloc(e, &P.L, nLall));
     CU_TRY(cudaMemset(P.L, 0, nLall * sizeof(double)));  // the idle slots of a tile travel with it: keep them defined
     if (cfg.welford) {
-      if (d > 32 || cfg.sequential || cfg.adaptInterval > SLGPU_JUMP_LOG_SLOTS)
-        return fail(SLGPU_E_CONFIG, "gpu.shaper \"welford\" needs nDims <= 32, the batched schedule and adaptInterval <= " + std::to_string(SLGPU_JUMP_LOG_SLOTS));
-      TRY_ST(dev_alloc(e, &P.jump_log, (size_t)cfg.adaptInterval * d * C));
+      if (d > 32 || cfg.sequential || cfg.recholEvery == 0 || (uint64_t)cfg.adaptInterval * cfg.recholEvery > SLGPU_JUMP_LOG_SLOTS)
+        return fail(SLGPU_E_CONFIG, "gpu.shaper \"welford\" needs nDims <= 32, the batched schedule and adaptInterval * recholEvery <= " + std::to_string(SLGPU_JUMP_LOG_SLOTS));
+      TRY_ST(dev_alloc(e, &P.jump_log, (size_t)cfg.adaptInterval * cfg.recholEvery * d * C));
       TRY_ST(dev_alloc(e, &P.moment, nLall));
       CU_TRY(cudaMemset(P.moment, 0, nLall * sizeof(double)));
       TRY_ST(dev_alloc(e, &P.chol_dirty, C));
@@ -1033,7 +1036,7 @@ static slgpu_status create_from_settings(const Settings& cfg, const char* plugin
     if (cfg.welford) {
       e->state.push_back({"moment", P.moment, nLall * sizeof(double)});
       e->state.push_back({"chol_dirty", P.chol_dirty, C});
-      e->state.push_back({"jump_log", P.jump_log, (size_t)cfg.adaptInterval * d * C * sizeof(double)});
+      e->state.push_back({"jump_log", P.jump_log, (size_t)cfg.adaptInterval * cfg.recholEvery * d * C * sizeof(double)});
     }
     if (payload && payload_bytes) {
       TRY_ST(dev_alloc(e, (char**)&e->d_payload, payload_bytes));

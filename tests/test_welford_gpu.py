@@ -36,9 +36,9 @@ def test_refactorised_every_round_it_is_the_reference_update():
     assert n_updated >= 5
 
 
-def _demo_stats(shaper, rounds=6000, S=48):
+def _demo_stats(shaper, rounds=6000, S=48, **kw):
     w = configs.workload("config1", S=S)
-    with engine_for(w, seed=17, shaper=shaper, hostRingRounds=rounds + 8) as eng:
+    with engine_for(w, seed=17, shaper=shaper, hostRingRounds=rounds + 8, **kw) as eng:
         eng.init_chains()
         eng.step_rounds(rounds)
         rows = eng.drain().reshape(rounds + 1, S, w["d"] + 5)
@@ -63,19 +63,34 @@ def test_welford_samples_the_same_posterior():
     assert max(sw["rhat"]) < 1.05
 
 
-def test_welford_is_deterministic_and_resumes(tmp_path):
+def test_rechol_every_third_adapt_point_same_posterior_and_limits():
+    """gpu.recholEvery = 3: the factor is refreshed every 30 rounds instead of every 10 (the jump log holds the accepts in
+    between).  Same bounds as above; a product adaptInterval * recholEvery beyond the log's 32 slots is refused."""
+    x, sm = _demo_stats("welford", recholEvery=3)
+    assert abs(x[:, 0].mean()) < 0.03 and abs(x[:, 2].mean()) < 0.03
+    assert abs(x[:, 0].std() / 3 ** -0.5 - 1.0) < 0.03 and abs(x[:, 2].std() / 3 ** -0.5 - 1.0) < 0.03
+    assert abs(x[:, 1].mean() - (2.0 / (3.0 * np.pi)) ** 0.5) < 0.03
+    assert np.all(np.abs(np.array(sm["accept_rate"])[:3] - 0.234) < 0.03) and max(sm["rhat"]) < 1.05
+    w = configs.workload("config3", S=8)
+    with pytest.raises(SlgpuError) as ei:
+        engine_for(w, shaper="welford", recholEvery=4)  # 10 * 4 > 32
+    assert ei.value.status == 1  # E_CONFIG
+
+
+@pytest.mark.parametrize("every", [1, 3])
+def test_welford_is_deterministic_and_resumes(tmp_path, every):
     w = configs.workload("config3", S=16)
-    with engine_for(w, seed=3, shaper="welford") as eng:
+    with engine_for(w, seed=3, shaper="welford", recholEvery=every) as eng:
         eng.init_chains()
         eng.step_rounds(47)
         want = (eng.last_rows(), eng.shaper(9)[0], eng.drain())
     ck = str(tmp_path / "w.ck")
-    with engine_for(w, seed=3, shaper="welford") as eng:
+    with engine_for(w, seed=3, shaper="welford", recholEvery=every) as eng:
         eng.init_chains()
         eng.step_rounds(23)
         first = eng.drain()
         eng.save_state(ck)
-    with engine_for(w, seed=3, shaper="welford") as eng:
+    with engine_for(w, seed=3, shaper="welford", recholEvery=every) as eng:
         eng.load_state(ck)
         eng.step_rounds(24)
         got = (eng.last_rows(), eng.shaper(9)[0], np.concatenate([first, eng.drain()]))

@@ -16,6 +16,7 @@ ap.add_argument("--sink", default="device")
 ap.add_argument("--swap", type=int, default=0, help="override swapInterval")
 ap.add_argument("--mrl", type=int, default=64, help="gpu.maxRoundsPerLaunch")
 ap.add_argument("--shaper", default="reference", help="gpu.shaper: reference | welford (opt-in, not the reference's arithmetic)")
+ap.add_argument("--rechol-every", type=int, default=1, help="gpu.recholEvery (welford shaper)")
 ap.add_argument("--plugin", default=None, help="path of a plugin .so built from the same targets (development: A/B builds)")
 ap.add_argument("--coarse", action="store_true", help="no per-launch events (lets programmatic dependent launch overlap)")
 a = ap.parse_args()
@@ -24,7 +25,7 @@ if a.plugin:
 w = configs.workload(a.workload, S=a.stacks)
 if a.swap:
     w["swapInterval"] = a.swap
-with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLaunch=a.mrl, shaper=a.shaper), plugin=w["plugin"], payload=w["payload"]) as e:
+with Engine(configs.engine_config(w, sink=a.sink, overwrite=True, maxRoundsPerLaunch=a.mrl, shaper=a.shaper, **({"recholEvery": a.rechol_every} if a.shaper == "welford" else {})), plugin=w["plugin"], payload=w["payload"]) as e:
     e.init_chains()
     e.step_rounds(a.warm)
     e.sync()
