@@ -284,12 +284,12 @@ def _ess_of_rows(rows, d):
     return float(np.mean(per_stack)) / rounds
 
 
-def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000):
+def ess_per_cold_sample(device, stacks=128, warm=1000, rounds=4000, **gpu):
     """GPU arm: ESS per cold-chain sample from a side run of the same workload with fewer stacks; multiplied by cold
     samples/s it gives ESS/s."""
     from stateline_b200 import Engine, configs
     w = configs.workload(WORKLOAD, S=stacks)
-    cfg = configs.engine_config(w, sink="host", device=device, hostRingRounds=rounds + 16, seed=99)
+    cfg = configs.engine_config(w, sink="host", device=device, hostRingRounds=rounds + 16, seed=99, **gpu)
     with Engine(cfg, plugin=w["plugin"], payload=w["payload"]) as e:
         e.init_chains()
         e.step_rounds(warm)
@@ -856,6 +856,7 @@ def main():
                 out["modes"][key] = {
                     "value": S * T * K * R / (w_ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": w_ms / K, "rechol_every_adapt_points": every,
                     "accept_rate_timed_region": [float(v) for v in w_acc],
+                    "ess_per_cold_sample": None if args.no_ess else ess_per_cold_sample(local_rank, shaper="welford", recholEvery=every),
                     "note": "gpu.shaper \"welford\": accepted jumps are logged, folded into a second-moment matrix and re-factorised at every "
                             "n-th adapt point (rechol_kernel); NOT the reference's arithmetic (no bit parity; tests/test_welford_gpu.py "
                             "validates it statistically); the headline above is the reference-exact mode"}
