@@ -63,6 +63,24 @@ def test_welford_samples_the_same_posterior():
     assert max(sw["rhat"]) < 1.05
 
 
+def test_welford_on_the_double_well_d2():
+    """d = 2 (fewer matrix rows than re-Cholesky warps: two of the four warps own no row): the mode runs, adapts to the same
+    accept rates as the reference mode and sees the same second moments of the bimodal target (bounds: 0.03 / 5 %)."""
+    w = configs.workload("config2", S=64)
+    rounds, res = 3000, {}
+    for shaper in ("reference", "welford"):
+        with engine_for(w, seed=11, shaper=shaper, hostRingRounds=rounds + 8) as eng:
+            eng.init_chains()
+            eng.step_rounds(rounds)
+            rows = eng.drain().reshape(rounds + 1, 64, w["d"] + 5)
+            res[shaper] = (rows[rounds // 3:, :, :2].reshape(-1, 2), eng.summary())
+    (xr, sr), (xw, sw) = res["reference"], res["welford"]
+    assert np.all(np.isfinite(xw))
+    m2r, m2w = (xr ** 2).mean(axis=0), (xw ** 2).mean(axis=0)
+    assert np.all(np.abs(m2w / m2r - 1.0) < 0.05), (m2r, m2w)
+    assert np.all(np.abs(np.array(sw["accept_rate"])[:4] - np.array(sr["accept_rate"])[:4]) < 0.03)
+
+
 def test_rechol_every_third_adapt_point_same_posterior_and_limits():
     """gpu.recholEvery = 3: the factor is refreshed every 30 rounds instead of every 10 (the jump log holds the accepts in
     between).  Same bounds as above; a product adaptInterval * recholEvery beyond the log's 32 slots is refused."""
