@@ -147,3 +147,20 @@ def test_format_row_is_printf_g_for_every_kind_of_value():
         row = np.concatenate([v, [i % 2, i % 3]])
         want = ",".join("%g" % x for x in v) + ",%d,%d" % (i % 2, i % 3)
         assert sb.format_row(row, d) == want
+
+
+def test_build_digest_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch):
+    """The source hash that decides whether an in-tree .so is stale (and that ties profiles/pt_step_traffic.json to the
+    kernels it was measured on) must be the same wherever the tree is copied: the GPU boxes run from a scratch path."""
+    from stateline_b200 import build as B
+    src = os.path.join(B.PKG, "plugins", "builtin_targets.cu")
+    flags = B.ARCH + B.COMMON + ["-O3"]
+    here = B._digest([src] + B._plugin_headers(), flags)
+    monkeypatch.setattr(B, "ROOT", "/somewhere/else")
+    moved_flags = [f.replace(ROOT, "/somewhere/else") for f in flags]
+    assert B._digest([src] + B._plugin_headers(), moved_flags) == here
+    assert not any(h.endswith("slgpu.h") for h in B._plugin_headers())  # the host API is no part of a plugin build
+    if os.path.exists(B.TARGETS_SO + ".srchash"):
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "pt_step_traffic.json")))
+        assert traffic["plugin_digest"] == open(B.TARGETS_SO + ".srchash").read().strip()[:16], \
+            "profiles/pt_step_traffic.json was measured on other kernel sources: re-capture it (tools/make_profiles_r2.py)"
